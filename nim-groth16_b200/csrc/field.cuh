@@ -1,0 +1,492 @@
+// 254-bit Montgomery arithmetic for BN254 Fp / Fr (R = 2^256), 8 x 32-bit limbs.
+//
+// Replaces the constantine field layer the reference reaches through
+// groth16/bn128/fields.nim:23-28,110-133 (types + operator sugar) with sm_100a device code.
+// In-memory layout is the reference's: 32 little-endian bytes holding the Montgomery residue
+// (io.nim:87-92,103-114).
+//
+// Device path: even/odd accumulator chains on mad.lo.cc/madc.hi.cc (ptxas fuses each lo/hi
+// pair into one IMAD.WIDE.U32[.X]); see tools/emu_montmul2.py for the carry-exact model.
+// Host path (G16_HOST_EMU or plain g++): portable u64 code with identical results, used only
+// by tests/hostemu to check the formulas layered on top.  The shipped library has no host
+// compute path.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define G16_HD __host__ __device__ __forceinline__
+#define G16_D __device__ __forceinline__
+#else
+#define G16_HD inline
+#define G16_D inline
+#endif
+
+namespace g16 {
+
+// ---------------------------------------------------------------------------------------
+// moduli and derived constants (fields.nim:36-37)
+// ---------------------------------------------------------------------------------------
+struct FpParams {
+  static G16_HD constexpr uint32_t mod(int i) {
+    constexpr uint32_t m[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+                               0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return m[i];
+  }
+  static constexpr uint32_t INV = 0xe4866389u;  // -p^-1 mod 2^32
+  static G16_HD constexpr uint32_t one(int i) {  // 2^256 mod p  (io.nim:87)
+    constexpr uint32_t m[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                               0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return m[i];
+  }
+  static G16_HD constexpr uint32_t r2(int i) {  // 2^512 mod p
+    constexpr uint32_t m[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+                               0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+    return m[i];
+  }
+};
+
+struct FrParams {
+  static G16_HD constexpr uint32_t mod(int i) {
+    constexpr uint32_t m[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                               0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return m[i];
+  }
+  static constexpr uint32_t INV = 0xefffffffu;  // -r^-1 mod 2^32
+  static G16_HD constexpr uint32_t one(int i) {  // 2^256 mod r  (io.nim:91)
+    constexpr uint32_t m[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                               0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return m[i];
+  }
+  static G16_HD constexpr uint32_t r2(int i) {  // 2^512 mod r
+    constexpr uint32_t m[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                               0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+    return m[i];
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// field element
+// ---------------------------------------------------------------------------------------
+template <class P>
+struct alignas(16) Fe {
+  uint32_t v[8];
+  typedef P Params;
+
+  static G16_HD Fe zero() {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
+    return r;
+  }
+  static G16_HD Fe one() {  // Montgomery form of 1
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::one(i);
+    return r;
+  }
+  static G16_HD Fe rsquared() {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::r2(i);
+    return r;
+  }
+  static G16_HD Fe modulus() {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::mod(i);
+    return r;
+  }
+};
+
+typedef Fe<FpParams> Fp;
+typedef Fe<FrParams> Fr;
+
+template <class P>
+G16_HD bool fis_zero(const Fe<P>& a) {
+  uint32_t t = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) t |= a.v[i];
+  return t == 0;
+}
+
+template <class P>
+G16_HD bool feq(const Fe<P>& a, const Fe<P>& b) {
+  uint32_t t = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) t |= a.v[i] ^ b.v[i];
+  return t == 0;
+}
+
+
+#if defined(__CUDA_ARCH__)
+// Every carry chain is ONE asm statement: the CC flag is invisible to the compiler, so
+// separate statements could legally be reordered.
+// All operands that are written are "+r" (in place): with plain "=r" outputs the compiler may
+// give an output the register of an input that a later instruction of the block still reads.
+// t += b (no overflow: both < 2^254, or b is a masked modulus)
+G16_D void add8_ip(uint32_t* t, const uint32_t* b) {
+  asm("add.cc.u32 %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, %12;\n\t"
+      "addc.cc.u32 %5, %5, %13;\n\t"
+      "addc.cc.u32 %6, %6, %14;\n\t"
+      "addc.u32 %7, %7, %15;"
+      : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7])
+      : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+}
+// t -= b, returns 0xffffffff when the subtraction borrowed, else 0
+G16_D uint32_t sub8_ip(uint32_t* t, const uint32_t* b) {
+  uint32_t borrow;
+  asm("sub.cc.u32 %0, %0, %9;\n\t"
+      "subc.cc.u32 %1, %1, %10;\n\t"
+      "subc.cc.u32 %2, %2, %11;\n\t"
+      "subc.cc.u32 %3, %3, %12;\n\t"
+      "subc.cc.u32 %4, %4, %13;\n\t"
+      "subc.cc.u32 %5, %5, %14;\n\t"
+      "subc.cc.u32 %6, %6, %15;\n\t"
+      "subc.cc.u32 %7, %7, %16;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]),
+        "=r"(borrow)
+      : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+  return borrow;
+}
+// y0 += X[1];  X := (X >> 64) + {a1,a3,a5,a7} * b + carry      (see tools/emu_montmul2.py)
+G16_D void mad_row_shift(uint32_t* X, uint32_t& y0, uint32_t a1, uint32_t a3, uint32_t a5, uint32_t a7,
+                         uint32_t b) {
+  asm("add.cc.u32 %8, %8, %1;\n\t"
+      "madc.lo.cc.u32 %0, %9, %13, %2;\n\t"
+      "madc.hi.cc.u32 %1, %9, %13, %3;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %4;\n\t"
+      "madc.hi.cc.u32 %3, %10, %13, %5;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %6;\n\t"
+      "madc.hi.cc.u32 %5, %11, %13, %7;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, 0;\n\t"
+      "madc.hi.u32 %7, %12, %13, 0;"
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]),
+        "+r"(y0)
+      : "r"(a1), "r"(a3), "r"(a5), "r"(a7), "r"(b));
+}
+// Y += {a0,a2,a4,a6} * b ; x7 += carry-out
+G16_D void mad_row_carry(uint32_t* Y, uint32_t& x7, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6,
+                         uint32_t b) {
+  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7]),
+        "+r"(x7)
+      : "r"(a0), "r"(a2), "r"(a4), "r"(a6), "r"(b));
+}
+// X += {p1,p3,p5,p7} * m   (no carry-out by construction)
+G16_D void mad_row_nc(uint32_t* X, uint32_t p1, uint32_t p3, uint32_t p5, uint32_t p7, uint32_t m) {
+  asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+      "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+      "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+      "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+      "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+      "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+      "madc.hi.u32 %7, %11, %12, %7;"
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7])
+      : "r"(p1), "r"(p3), "r"(p5), "r"(p7), "r"(m));
+}
+// D += (E >> 32)  (E[0] == 0), 8 limbs, no carry-out
+G16_D void merge8_ip(uint32_t* D, const uint32_t* E) {
+  asm("add.cc.u32 %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, %12;\n\t"
+      "addc.cc.u32 %5, %5, %13;\n\t"
+      "addc.cc.u32 %6, %6, %14;\n\t"
+      "addc.u32 %7, %7, 0;"
+      : "+r"(D[0]), "+r"(D[1]), "+r"(D[2]), "+r"(D[3]), "+r"(D[4]), "+r"(D[5]), "+r"(D[6]), "+r"(D[7])
+      : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]));
+}
+#endif
+
+// ---------------------------------------------------------------------------------------
+// add / sub (inputs and outputs fully reduced: < modulus)
+// ---------------------------------------------------------------------------------------
+template <class P>
+G16_HD Fe<P> fadd(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> t, u;
+#if defined(__CUDA_ARCH__)
+  uint32_t m[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) m[i] = P::mod(i);
+  t = a;
+  add8_ip(t.v, b.v);
+  u = t;
+  uint32_t borrow = sub8_ip(u.v, m);
+#pragma unroll
+  for (int i = 0; i < 8; i++) t.v[i] = borrow ? t.v[i] : u.v[i];
+  return t;
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.v[i] + b.v[i];
+    t.v[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  int64_t bw = 0;
+  for (int i = 0; i < 8; i++) {
+    bw += (int64_t)t.v[i] - (int64_t)P::mod(i);
+    u.v[i] = (uint32_t)bw;
+    bw >>= 32;
+  }
+  return bw ? t : u;
+#endif
+}
+
+template <class P>
+G16_HD Fe<P> fsub(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> t;
+#if defined(__CUDA_ARCH__)
+  t = a;
+  uint32_t borrow = sub8_ip(t.v, b.v);
+  uint32_t m[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) m[i] = P::mod(i) & borrow;
+  add8_ip(t.v, m);
+  return t;
+#else
+  int64_t bw = 0;
+  for (int i = 0; i < 8; i++) {
+    bw += (int64_t)a.v[i] - (int64_t)b.v[i];
+    t.v[i] = (uint32_t)bw;
+    bw >>= 32;
+  }
+  if (bw) {
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+      c += (uint64_t)t.v[i] + P::mod(i);
+      t.v[i] = (uint32_t)c;
+      c >>= 32;
+    }
+  }
+  return t;
+#endif
+}
+
+template <class P>
+G16_HD Fe<P> fneg(const Fe<P>& a) {
+  return fis_zero(a) ? a : fsub(Fe<P>::modulus(), a);
+}
+
+template <class P>
+G16_HD Fe<P> fdbl(const Fe<P>& a) {
+  return fadd(a, a);
+}
+
+// a/2 mod p (ntt.nim:121 div2)
+template <class P>
+G16_HD Fe<P> fhalve(const Fe<P>& a) {
+  Fe<P> t = a;
+  uint64_t c = 0;
+  uint32_t odd = 0u - (a.v[0] & 1u);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)t.v[i] + (P::mod(i) & odd);
+    t.v[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#pragma unroll
+  for (int i = 0; i < 7; i++) t.v[i] = (t.v[i] >> 1) | (t.v[i + 1] << 31);
+  t.v[7] = (t.v[7] >> 1) | ((uint32_t)c << 31);
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------
+// Montgomery multiplication: returns a*b/2^256 mod p, fully reduced.
+// ---------------------------------------------------------------------------------------
+template <class P>
+G16_HD Fe<P> fmul(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> r;
+#if defined(__CUDA_ARCH__)
+  // t[0] / t[1] alternate between the "even" (column k) and "odd" (column k+1) roles.
+  uint32_t t[2][8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) t[0][k] = t[1][k] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t* X = t[i & 1];        // odd-aligned array of this iteration (shifted in place)
+    uint32_t* Y = t[(i + 1) & 1];  // even-aligned array of this iteration
+    const uint32_t bi = b.v[i];
+    mad_row_shift(X, Y[0], a.v[1], a.v[3], a.v[5], a.v[7], bi);
+    mad_row_carry(Y, X[7], a.v[0], a.v[2], a.v[4], a.v[6], bi);
+    const uint32_t m = Y[0] * P::INV;
+    mad_row_nc(X, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+    mad_row_carry(Y, X[7], P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);
+  }
+  // iteration 7 had X = t[1] (odd role) and Y = t[0] (even role, limb 0 now zero)
+  merge8_ip(t[1], t[0]);
+#pragma unroll
+  for (int k = 0; k < 8; k++) r.v[k] = t[1][k];
+  Fe<P> u = r;
+  uint32_t pm[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) pm[k] = P::mod(k);
+  uint32_t borrow = sub8_ip(u.v, pm);
+#pragma unroll
+  for (int k = 0; k < 8; k++) r.v[k] = borrow ? r.v[k] : u.v[k];
+  return r;
+#else
+  // portable CIOS on 32-bit limbs with 64-bit accumulators
+  uint32_t t[10];
+  for (int k = 0; k < 10; k++) t[k] = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < 8; j++) {
+      c += (uint64_t)a.v[j] * b.v[i] + t[j];
+      t[j] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[8];
+    t[8] = (uint32_t)c;
+    t[9] = (uint32_t)(c >> 32);
+    uint32_t m = t[0] * P::INV;
+    c = (uint64_t)m * P::mod(0) + t[0];
+    c >>= 32;
+    for (int j = 1; j < 8; j++) {
+      c += (uint64_t)m * P::mod(j) + t[j];
+      t[j - 1] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[8];
+    t[7] = (uint32_t)c;
+    t[8] = t[9] + (uint32_t)(c >> 32);
+  }
+  for (int k = 0; k < 8; k++) r.v[k] = t[k];
+  Fe<P> u;
+  int64_t bw = 0;
+  for (int k = 0; k < 8; k++) {
+    bw += (int64_t)r.v[k] - (int64_t)P::mod(k);
+    u.v[k] = (uint32_t)bw;
+    bw >>= 32;
+  }
+  return (bw && !t[8]) ? r : u;
+#endif
+}
+
+template <class P>
+G16_HD Fe<P> fsqr(const Fe<P>& a) {
+  return fmul(a, a);
+}
+
+// Montgomery form <-> standard form
+template <class P>
+G16_HD Fe<P> to_mont(const Fe<P>& a) {
+  return fmul(a, Fe<P>::rsquared());
+}
+template <class P>
+G16_HD Fe<P> from_mont(const Fe<P>& a) {
+  Fe<P> one = Fe<P>::zero();
+  one.v[0] = 1;
+  return fmul(a, one);
+}
+
+// a^(p-2) (Fermat); a = 0 -> 0.  Not unrolled: it is used once per MSM / proof, not per element.
+template <class P>
+G16_HD Fe<P> finv(const Fe<P>& a) {
+  uint32_t e[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) e[i] = P::mod(i);
+  e[0] -= 2;  // both moduli end in ...01 / ...47: no borrow
+  Fe<P> acc = Fe<P>::one();
+#pragma unroll 1
+  for (int i = 253; i >= 0; i--) {
+    acc = fsqr(acc);
+    if ((e[i >> 5] >> (i & 31)) & 1u) acc = fmul(acc, a);
+  }
+  return acc;
+}
+
+// small-exponent power (fields.nim:139-147 smallPowFr)
+template <class P>
+G16_HD Fe<P> fpow_u64(const Fe<P>& base, uint64_t e) {
+  Fe<P> a = Fe<P>::one();
+  Fe<P> s = base;
+#pragma unroll 1
+  while (e) {
+    if (e & 1) a = fmul(a, s);
+    e >>= 1;
+    s = fsqr(s);
+  }
+  return a;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fp2 = Fp[u]/(u^2 + 1)   (fields.nim:27,30-32; c0 then c1 in memory)
+// ---------------------------------------------------------------------------------------
+struct alignas(16) Fp2 {
+  Fp c0, c1;
+  static G16_HD Fp2 zero() {
+    Fp2 r;
+    r.c0 = Fp::zero();
+    r.c1 = Fp::zero();
+    return r;
+  }
+  static G16_HD Fp2 one() {
+    Fp2 r;
+    r.c0 = Fp::one();
+    r.c1 = Fp::zero();
+    return r;
+  }
+};
+
+G16_HD bool fis_zero(const Fp2& a) { return fis_zero(a.c0) && fis_zero(a.c1); }
+G16_HD bool feq(const Fp2& a, const Fp2& b) { return feq(a.c0, b.c0) && feq(a.c1, b.c1); }
+G16_HD Fp2 fadd(const Fp2& a, const Fp2& b) {
+  Fp2 r;
+  r.c0 = fadd(a.c0, b.c0);
+  r.c1 = fadd(a.c1, b.c1);
+  return r;
+}
+G16_HD Fp2 fsub(const Fp2& a, const Fp2& b) {
+  Fp2 r;
+  r.c0 = fsub(a.c0, b.c0);
+  r.c1 = fsub(a.c1, b.c1);
+  return r;
+}
+G16_HD Fp2 fneg(const Fp2& a) {
+  Fp2 r;
+  r.c0 = fneg(a.c0);
+  r.c1 = fneg(a.c1);
+  return r;
+}
+G16_HD Fp2 fdbl(const Fp2& a) { return fadd(a, a); }
+G16_HD Fp2 fmul(const Fp2& a, const Fp2& b) {  // Karatsuba, 3 Fp mul
+  Fp t0 = fmul(a.c0, b.c0);
+  Fp t1 = fmul(a.c1, b.c1);
+  Fp s = fmul(fadd(a.c0, a.c1), fadd(b.c0, b.c1));
+  Fp2 r;
+  r.c0 = fsub(t0, t1);
+  r.c1 = fsub(fsub(s, t0), t1);
+  return r;
+}
+G16_HD Fp2 fsqr(const Fp2& a) {  // 2 Fp mul
+  Fp t = fmul(a.c0, a.c1);
+  Fp2 r;
+  r.c0 = fmul(fadd(a.c0, a.c1), fsub(a.c0, a.c1));
+  r.c1 = fdbl(t);
+  return r;
+}
+G16_HD Fp2 finv(const Fp2& a) {
+  Fp d = finv(fadd(fsqr(a.c0), fsqr(a.c1)));
+  Fp2 r;
+  r.c0 = fmul(a.c0, d);
+  r.c1 = fneg(fmul(a.c1, d));
+  return r;
+}
+
+}  // namespace g16
