@@ -1,0 +1,240 @@
+/* g16b200 -- C ABI of the B200 (sm_100a) Groth16 proving backend for codex-storage/nim-groth16.
+ *
+ * The reference (/root/reference, pure Nim) has no FFI of its own: the boundary is the set of Nim
+ * procs on the hot path.  Every entry point below names the reference proc it replaces (file:line,
+ * relative to the reference root); INTEGRATION.md shows the `importc` binding for each.
+ *
+ * Conventions:
+ *   - Field elements are 32 little-endian bytes = 4 x uint64 limbs.  "mont" = Montgomery residue with
+ *     R = 2^256 (constantine's in-memory Fr/Fp, and the point sections of a .zkey, io.nim:103-131);
+ *     "std" = the plain integer (.wtns / .r1cs, io.nim:141-145).
+ *   - G1 affine = x, y (2 x Fp, 64 bytes); G2 affine = x.c0, x.c1, y.c0, y.c1 (128 bytes); infinity is
+ *     the all-zero encoding (curves.nim:49-50).  Points are always Montgomery.
+ *   - All calls are synchronous; the caller owns every buffer; inputs are only read during the call.
+ *   - Return value 0 = ok; non-zero = failure, text from g16_last_error() (the Nim shim raises
+ *     AssertionDefect, matching the reference's assert()s, e.g. msm.nim:97, prover.nim:236).
+ *   - One caller thread per context.  `nthreads` of the reference signatures is a host-side hint with
+ *     no meaning on the GPU and is therefore absent here.
+ *   - There is no CPU fallback: every function fails if no sm_100 device is usable.
+ */
+#ifndef G16B200_H
+#define G16B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G16_OK 0
+#define G16_ERR_ARG 1      /* precondition violated (the reference would raise AssertionDefect) */
+#define G16_ERR_CUDA 2     /* CUDA runtime failure, or no usable device */
+
+#define G16_FORM_MONT 0    /* scalars are Montgomery residues (Nim seq[Fr] payload) */
+#define G16_FORM_STD 1     /* scalars are standard-form integers (.wtns payload) */
+
+#define G16_FLAVOUR_JENSGROTH 0   /* zkey_types.nim:11 */
+#define G16_FLAVOUR_SNARKJS 1     /* zkey_types.nim:12 */
+
+#define G16_COEFF_PACKED44_R2 0   /* .zkey section 4 record: u32 m,row,col + 32 B value*R^2 (zkey.nim:169-188) */
+#define G16_COEFF_STRUCT48_MONT 1 /* g16_coeff below: value*R (the reference's in-memory Coeff, zkey_types.nim:48-52) */
+
+#define G16_MEM_HOST 0
+#define G16_MEM_DEVICE 1
+
+const char* g16_last_error(void);
+/* ABI version, device selection (one process per GPU; default device = cudaGetDevice()). */
+int g16_version(void);
+int g16_set_device(int device);
+int g16_device_count(int* count);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fine-grained level: one call per reference proc, host buffers in and out.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* msmMultiThreadedG1 (groth16/bn128/msm.nim:89-124) / msmConstantineG1 (msm.nim:35-59).
+ * out = sum_i scalars[i] * points[i], affine Montgomery, (0,0) for infinity.  n may be 0. */
+int g16_msm_g1(const uint64_t* scalars, int scalar_form, const uint64_t* points, size_t n, uint64_t out[8]);
+
+/* msmMultiThreadedG2 (msm.nim:128-158) / msmConstantineG2 (msm.nim:63-83). points: n x 16 limbs. */
+int g16_msm_g2(const uint64_t* scalars, int scalar_form, const uint64_t* points, size_t n, uint64_t out[16]);
+
+/* forwardNTT (groth16/math/ntt.nim:55-77) / inverseNTT (ntt.nim:139-161): natural order in and out,
+ * Montgomery in and out, domain = createDomain(2^log_n) (domain.nim:28-46), inverse includes 1/n. */
+int g16_ntt_fr(const uint64_t* in, uint64_t* out, int log_n, int inverse);
+
+/* computeSnarkjsScalarCoeffs (groth16/prover.nim:158-181) for flavour = G16_FLAVOUR_SNARKJS,
+ * computeQuotientPointwise (prover.nim:118-148) for G16_FLAVOUR_JENSGROTH.
+ * az, bz: 2^log_n Montgomery elements each; Cz = Az o Bz is derived inside (prover.nim:69-71). */
+int g16_quotient(const uint64_t* az, const uint64_t* bz, int log_n, int flavour, uint64_t* qs_out);
+
+typedef struct g16_coeff {   /* mirrors Coeff (zkey_types.nim:48-52) */
+  uint32_t matrix;           /* 0 = A, 1 = B; 2 (= C) is rejected like prover.nim:67 */
+  uint32_t row;
+  uint32_t col;
+  uint32_t reserved;
+  uint64_t value[4];         /* Montgomery */
+} g16_coeff;
+
+/* buildABC (groth16/prover.nim:56-73).  coeffs: nnz records of `coeff_format`; witness: m elements of
+ * `witness_form`; az/bz/cz: 2^log_n Montgomery elements each. */
+int g16_build_abc(const void* coeffs, size_t nnz, int coeff_format, const uint64_t* witness, int witness_form,
+                  size_t m, int log_n, uint64_t* az, uint64_t* bz, uint64_t* cz);
+
+/* ------------------------------------------------------------------------------------------------
+ * Coarse level: resident prover context = generateProofWithMask (groth16/prover.nim:215-304).
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct g16_zkey_view {        /* ZKey (zkey_types.nim:54-60) as raw arrays */
+  uint32_t nvars;                     /* GrothHeader.nvars  (zkey_types.nim:19) */
+  uint32_t npubs;                     /* GrothHeader.npubs  */
+  uint32_t log_domain;                /* GrothHeader.logDomainSize */
+  uint32_t flavour;                   /* G16_FLAVOUR_* */
+  uint32_t coeff_format;              /* G16_COEFF_* */
+  uint32_t mem_kind;                  /* G16_MEM_HOST / G16_MEM_DEVICE for the pointers below */
+  uint64_t ncoeffs;
+  const void* coeffs;                 /* ZKey.coeffs */
+  const uint64_t* points_a1;          /* nvars G1            (ProverPoints, zkey_types.nim:34-40) */
+  const uint64_t* points_b1;          /* nvars G1 */
+  const uint64_t* points_b2;          /* nvars G2 */
+  const uint64_t* points_c1;          /* nvars - npubs - 1 G1 */
+  const uint64_t* points_h1;          /* 2^log_domain G1 */
+  uint64_t alpha1[8];                 /* SpecPoints (zkey_types.nim:24-31) */
+  uint64_t beta1[8];
+  uint64_t beta2[16];
+  uint64_t delta1[8];
+  uint64_t delta2[16];
+} g16_zkey_view;
+
+typedef struct g16_proof {            /* Proof (prover.nim:38-43) minus publicIO (= witness[0..npubs]) */
+  uint64_t pi_a[8];
+  uint64_t pi_b[16];
+  uint64_t pi_c[8];
+} g16_proof;
+
+typedef struct g16_stats {            /* device-side milliseconds under the reference's timing labels */
+  float ms_h2d;                       /* witness upload */
+  float ms_abc;                       /* "building 'ABC'"                    prover.nim:244 */
+  float ms_quotient;                  /* "computing the quotient (FFTs)"     prover.nim:249 */
+  float ms_msm_a;                     /* "computing pi_A (G1 MSM)"           prover.nim:279 */
+  float ms_msm_b1;                    /* "computing rho (G1 MSM)"            prover.nim:285 */
+  float ms_msm_b2;                    /* "computing pi_B (G2 MSM)"           prover.nim:291 */
+  float ms_msm_h;                     /* "computing pi_C (2x G1 MSM)": H     prover.nim:297 */
+  float ms_msm_c;                     /*                               and C */
+  float ms_assemble;
+  float ms_total;
+  uint32_t kernel_launches;           /* launches of this library's own kernels during the call */
+  uint32_t reserved;
+} g16_stats;
+
+/* partial MSM results of one point-range shard, affine Montgomery: A1, B1, H1, C1 (G1) and B2 (G2) */
+typedef struct g16_partials {
+  uint64_t msm_a1[8];
+  uint64_t msm_b1[8];
+  uint64_t msm_h1[8];
+  uint64_t msm_c1[8];
+  uint64_t msm_b2[16];
+} g16_partials;
+
+typedef struct g16_ctx g16_ctx;
+
+/* Uploads (once) the prover points and the coefficient list of a zkey.  shard_index / shard_count
+ * select the contiguous point range [N*k/G, N*(k+1)/G) of every MSM, the chunking of msm.nim:107-115;
+ * pass 0, 1 for the whole key on one GPU. */
+int g16_ctx_create(const g16_zkey_view* zkey, int shard_index, int shard_count, g16_ctx** out);
+void g16_ctx_destroy(g16_ctx* ctx);
+
+/* generateProofWithMask (prover.nim:215-304).  witness: nvars elements of `witness_form` (host);
+ * r, s: the mask (prover.nim:211-213) as standard-form integers.  Requires shard_count == 1. */
+int g16_prove(g16_ctx* ctx, const uint64_t* witness, int witness_form, const uint64_t r_std[4],
+              const uint64_t s_std[4], g16_proof* proof, g16_stats* stats);
+
+/* Same with the witness already resident in device memory (standard form). */
+int g16_prove_dev(g16_ctx* ctx, const void* witness_std_dev, const uint64_t r_std[4], const uint64_t s_std[4],
+                  g16_proof* proof, g16_stats* stats);
+
+/* Multi-GPU split of the same computation (msm.nim:107-119 across devices):
+ *   every rank:  g16_prove_partials -> its five partial sums (device buffer of sizeof(g16_partials)),
+ *   exchange:    all-gather of those 384-byte records (NCCL / peer copy, done by the host side),
+ *   any rank:    g16_prove_finish over the gathered records -> the proof. */
+int g16_prove_partials(g16_ctx* ctx, const uint64_t* witness, int witness_form, int witness_mem_kind,
+                       void* partials_dev, g16_stats* stats);
+int g16_prove_finish(g16_ctx* ctx, const void* gathered_partials_dev, int count, const uint64_t r_std[4],
+                     const uint64_t s_std[4], g16_proof* proof);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident variants used by the benchmarks (inputs already in HBM; `stream` is a cudaStream_t).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct g16_msm_plan g16_msm_plan;   /* reusable workspace for one MSM shape */
+int g16_msm_plan_create(int g2, size_t max_n, int window_bits /*0 = auto*/, g16_msm_plan** out);
+void g16_msm_plan_destroy(g16_msm_plan* plan);
+/* result_dev: XYZZ accumulator (128 B for G1, 256 B for G2) */
+int g16_msm_dev(g16_msm_plan* plan, const void* scalars_dev, int scalar_form, const void* points_dev, size_t n,
+                void* result_xyzz_dev, void* stream);
+int g16_msm_result_to_affine(int g2, const void* result_xyzz_dev, int count, uint64_t* out_host);
+int g16_msm_plan_info(const g16_msm_plan* plan, int* window_bits, int* num_windows, size_t* workspace_bytes);
+
+/* in_dev/out_dev/work_dev: 2^log_n elements each (out distinct from the others) */
+int g16_ntt_fr_dev(const void* in_dev, void* out_dev, void* work_dev, int log_n, int inverse, void* stream);
+/* abc_dev: 3 * 2^log_n elements [Az | Bz | scratch], clobbered; qs_dev: 2^log_n elements */
+int g16_quotient_dev(void* abc_dev, void* qs_dev, int log_n, int flavour, void* stream);
+int g16_ntt_prepare(int log_n);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fake trusted setup on the GPU (groth16/fake_setup.nim:201-326 fakeCircuitSetup) -- fixture generator
+ * and `--setup` backend.  Matrices are COO triplets (row, col, standard-form value) of the R1CS
+ * (r1cs.nim:64-80), *without* the dummy public rows (they are added inside, fake_setup.nim:182-185).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct g16_r1cs_view {
+  uint32_t nvars;          /* cfg.nWires */
+  uint32_t npubs;          /* nPubIn + nPubOut */
+  uint32_t neqs;           /* constraints.len */
+  uint32_t flavour;
+  uint64_t nnz[3];         /* A, B, C */
+  const uint32_t* rows[3];
+  const uint32_t* cols[3];
+  const uint64_t* vals[3]; /* nnz x 4 limbs, standard form */
+} g16_r1cs_view;
+
+typedef struct g16_toxic {   /* ToxicWaste (fake_setup.nim:24-30), standard form */
+  uint64_t alpha[4], beta[4], gamma[4], delta[4], tau[4];
+} g16_toxic;
+
+typedef struct g16_setup_out {       /* host buffers sized by the caller; any pointer may be NULL */
+  uint64_t* points_a1;               /* nvars G1 */
+  uint64_t* points_b1;               /* nvars G1 */
+  uint64_t* points_b2;               /* nvars G2 */
+  uint64_t* points_c1;               /* nvars - npubs - 1 G1 */
+  uint64_t* points_h1;               /* domain G1 */
+  uint64_t* points_ic;               /* npubs + 1 G1 */
+  uint64_t* spec;                    /* alpha1, beta1, delta1 (G1) then beta2, gamma2, delta2 (G2): 3*8 + 3*16 limbs */
+  uint64_t* dlog_a;                  /* nvars standard-form scalars a_j  (closed-form oracle) */
+  uint64_t* dlog_b;                  /* nvars */
+  uint64_t* dlog_k;                  /* nvars - npubs - 1 */
+  uint64_t* dlog_h;                  /* domain */
+  uint64_t* dlog_ic;                 /* npubs + 1 */
+} g16_setup_out;
+
+int g16_fake_setup(const g16_r1cs_view* r1cs, const g16_toxic* toxic, uint32_t* log_domain_out, g16_setup_out* out);
+
+/* k_i * g1 / k_i * g2 for standard-form scalars (curves.nim:182-196 `**` on the generators) */
+int g16_fixed_base_g1(const uint64_t* scalars_std, size_t n, uint64_t* points_out);
+int g16_fixed_base_g2(const uint64_t* scalars_std, size_t n, uint64_t* points_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Diagnostics
+ * ---------------------------------------------------------------------------------------------- */
+/* device field/curve self-test against the library's portable host arithmetic; 0 = pass */
+int g16_selftest(uint32_t seed, uint32_t cases);
+/* integer-pipe microbenchmark: sustained 32-bit multiply-add rate of all SMs.
+ * kind 0 = mad.lo.u32, 1 = mad.hi.u32, 2 = lo/hi carry pairs (IMAD.WIDE.X), 3 = full Montgomery multiplies.
+ * Reports operations (MAC32, or modmuls for kind 3) per second. */
+int g16_bench_int_pipe(int kind, double* ops_per_sec, float* ms);
+/* number of kernels this library has launched in this process */
+uint64_t g16_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G16B200_H */

@@ -1,0 +1,407 @@
+// extern "C" boundary of libg16b200.so (declared in include/g16b200.h).
+// Plain pointers and sizes only; every function returns a status code and never throws.
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <string.h>
+#include "../../include/g16b200.h"
+#include "abc.cuh"
+#include "common.cuh"
+#include "ec.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+#include "prover.cuh"
+
+namespace g16 {
+
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& msg) { t_last_error = msg; }
+const char* get_last_error() { return t_last_error.c_str(); }
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void fake_setup(const g16_r1cs_view& r, const g16_toxic& toxic, uint32_t* log_domain_out, g16_setup_out& out);
+template <class F>
+void fixed_base_mul(const Fr* scalars_dev, size_t n, Affine<F>* out_dev, cudaStream_t stream);
+int selftest_run(uint32_t seed, uint32_t cases);
+void bench_int_pipe(int kind, double* ops_per_sec, float* ms);
+
+static void require_device() {
+  static std::once_flag once;
+  static int ok = 0;
+  static std::string why;
+  std::call_once(once, [] {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      why = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+      return;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+      why = "cudaGetDeviceProperties failed";
+      return;
+    }
+    if (p.major != 10) {
+      why = std::string("device '") + p.name + "' is not sm_100 (compute capability " + std::to_string(p.major) +
+            "." + std::to_string(p.minor) + "); the library is built for sm_100a only";
+      return;
+    }
+    ok = 1;
+  });
+  if (!ok) throw Error(G16_ERR_CUDA, why);
+}
+
+template <class Fn>
+static int guard(Fn&& fn) {
+  try {
+    require_device();
+    fn();
+    return G16_OK;
+  } catch (const Error& e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return G16_ERR_CUDA;
+  }
+}
+
+// per-thread scratch of the fine-grained host-buffer calls (grow-only, reused between calls)
+struct Scratch {
+  DevBuf a, b, c, d, res;
+  Msm<Fp> msm1;
+  Msm<Fp2> msm2;
+  cudaStream_t stream = nullptr;
+  cudaStream_t s() {
+    if (!stream) G16_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    return stream;
+  }
+};
+static Scratch& scratch() {
+  static thread_local std::unique_ptr<Scratch> s;
+  if (!s) s.reset(new Scratch());
+  return *s;
+}
+
+template <class F>
+static void msm_host(Msm<F>& eng, const uint64_t* scalars, int form, const uint64_t* points, size_t n, uint64_t* out) {
+  G16_REQUIRE(form == G16_FORM_MONT || form == G16_FORM_STD, "unknown scalar form");
+  G16_REQUIRE(out != nullptr, "output is null");
+  G16_REQUIRE(n == 0 || (scalars != nullptr && points != nullptr), "incompatible sequence lengths");   // msm.nim:97
+  Scratch& sc = scratch();
+  cudaStream_t s = sc.s();
+  sc.a.ensure(n * sizeof(Fr) + 16);
+  sc.b.ensure(n * sizeof(Affine<F>) + 16);
+  sc.res.ensure(sizeof(XYZZ<F>) + sizeof(Affine<F>));
+  if (n) {
+    G16_CUDA(cudaMemcpyAsync(sc.a.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    G16_CUDA(cudaMemcpyAsync(sc.b.p, points, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, s));
+  }
+  XYZZ<F>* r = sc.res.as<XYZZ<F>>();
+  Affine<F>* ra = reinterpret_cast<Affine<F>*>(r + 1);
+  eng.run(sc.a.as<Fr>(), form == G16_FORM_MONT, sc.b.as<Affine<F>>(), n, r, s);
+  xyzz_sum_to_affine<F>(r, 1, ra, s);
+  G16_CUDA(cudaMemcpyAsync(out, ra, sizeof(Affine<F>), cudaMemcpyDeviceToHost, s));
+  G16_CUDA(cudaStreamSynchronize(s));
+}
+
+template <class F>
+static void fixed_base_host(const uint64_t* scalars, size_t n, uint64_t* out) {
+  G16_REQUIRE(n == 0 || (scalars && out), "null argument");
+  if (!n) return;
+  Scratch& sc = scratch();
+  cudaStream_t s = sc.s();
+  sc.a.ensure(n * sizeof(Fr));
+  sc.b.ensure(n * sizeof(Affine<F>));
+  G16_CUDA(cudaMemcpyAsync(sc.a.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+  fixed_base_mul<F>(sc.a.as<Fr>(), n, sc.b.as<Affine<F>>(), s);
+  G16_CUDA(cudaMemcpyAsync(out, sc.b.p, n * sizeof(Affine<F>), cudaMemcpyDeviceToHost, s));
+  G16_CUDA(cudaStreamSynchronize(s));
+}
+}  // namespace g16
+
+using namespace g16;
+
+struct g16_ctx {
+  std::unique_ptr<Prover> prover;
+};
+
+struct g16_msm_plan {
+  int g2 = 0;
+  int window = 0;
+  size_t max_n = 0;
+  Msm<Fp> m1;
+  Msm<Fp2> m2;
+};
+
+extern "C" {
+
+const char* g16_last_error(void) { return get_last_error(); }
+int g16_version(void) { return 1; }
+uint64_t g16_kernel_launch_count(void) { return g_launches.load(); }
+
+int g16_set_device(int device) {
+  return guard([&] { G16_CUDA(cudaSetDevice(device)); });
+}
+int g16_device_count(int* count) {
+  return guard([&] {
+    G16_REQUIRE(count != nullptr, "count is null");
+    G16_CUDA(cudaGetDeviceCount(count));
+  });
+}
+
+int g16_msm_g1(const uint64_t* scalars, int scalar_form, const uint64_t* points, size_t n, uint64_t out[8]) {
+  return guard([&] { msm_host<Fp>(scratch().msm1, scalars, scalar_form, points, n, out); });
+}
+int g16_msm_g2(const uint64_t* scalars, int scalar_form, const uint64_t* points, size_t n, uint64_t out[16]) {
+  return guard([&] { msm_host<Fp2>(scratch().msm2, scalars, scalar_form, points, n, out); });
+}
+
+int g16_ntt_fr(const uint64_t* in, uint64_t* out, int log_n, int inverse) {
+  return guard([&] {
+    G16_REQUIRE(in != nullptr && out != nullptr, "input must have the same size as the domain");   // ntt.nim:57
+    G16_REQUIRE(log_n >= 0 && log_n <= 26, "domain must have a power-of-two size");                  // ntt.nim:56
+    size_t n = (size_t)1 << log_n;
+    if (log_n == 0) {                      // ntt.nim:24-26: the size-1 transform is the identity
+      memcpy(out, in, sizeof(Fr));
+      return;
+    }
+    Scratch& sc = scratch();
+    cudaStream_t s = sc.s();
+    sc.a.ensure(n * sizeof(Fr));
+    sc.b.ensure(n * sizeof(Fr));
+    G16_CUDA(cudaMemcpyAsync(sc.a.p, in, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    ntt_natural(sc.a.as<Fr>(), sc.b.as<Fr>(), sc.a.as<Fr>(), log_n, inverse != 0, s);
+    G16_CUDA(cudaMemcpyAsync(out, sc.b.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    G16_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int g16_quotient(const uint64_t* az, const uint64_t* bz, int log_n, int flavour, uint64_t* qs_out) {
+  return guard([&] {
+    G16_REQUIRE(az && bz && qs_out, "null vector");
+    G16_REQUIRE(log_n >= 1 && log_n <= 26, "domain must be 2^1 .. 2^26 (prover.nim:101 needs n >= 2)");
+    G16_REQUIRE(flavour == G16_FLAVOUR_JENSGROTH || flavour == G16_FLAVOUR_SNARKJS, "unknown flavour");
+    size_t n = (size_t)1 << log_n;
+    Scratch& sc = scratch();
+    cudaStream_t s = sc.s();
+    sc.a.ensure(3 * n * sizeof(Fr));
+    sc.b.ensure(n * sizeof(Fr));
+    G16_CUDA(cudaMemcpyAsync(sc.a.p, az, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    G16_CUDA(cudaMemcpyAsync(sc.a.as<Fr>() + n, bz, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    quotient(sc.a.as<Fr>(), sc.b.as<Fr>(), log_n, flavour, s);
+    G16_CUDA(cudaMemcpyAsync(qs_out, sc.b.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    G16_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int g16_build_abc(const void* coeffs, size_t nnz, int coeff_format, const uint64_t* witness, int witness_form,
+                  size_t m, int log_n, uint64_t* az, uint64_t* bz, uint64_t* cz) {
+  return guard([&] {
+    G16_REQUIRE(log_n >= 0 && log_n <= 26, "domain must have a power-of-two size");
+    G16_REQUIRE(nnz == 0 || coeffs != nullptr, "coefficient list is null");
+    G16_REQUIRE(m == 0 || witness != nullptr, "witness is null");
+    G16_REQUIRE(witness_form == G16_FORM_MONT || witness_form == G16_FORM_STD, "unknown witness form");
+    G16_REQUIRE(coeff_format == G16_COEFF_PACKED44_R2 || coeff_format == G16_COEFF_STRUCT48_MONT,
+                "unknown coefficient record format");
+    size_t n = (size_t)1 << log_n;
+    size_t rec = coeff_format == G16_COEFF_PACKED44_R2 ? 44 : 48;
+    Scratch& sc = scratch();
+    cudaStream_t s = sc.s();
+    sc.a.ensure(nnz * rec + 16);
+    sc.b.ensure(m * sizeof(Fr) + 32);
+    sc.c.ensure(3 * n * sizeof(Fr));
+    if (nnz) G16_CUDA(cudaMemcpyAsync(sc.a.p, coeffs, nnz * rec, cudaMemcpyHostToDevice, s));
+    if (m) G16_CUDA(cudaMemcpyAsync(sc.b.p, witness, m * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    if (witness_form == G16_FORM_MONT) fr_from_mont(sc.b.as<Fr>(), sc.b.as<Fr>(), m, s);
+    SparseCsr csr;
+    coeffs_to_csr(csr, sc.a.p, nnz, coeff_format, log_n, m, s);
+    build_abc(csr, sc.b.as<Fr>(), sc.c.as<Fr>(), log_n, s);
+    if (az) G16_CUDA(cudaMemcpyAsync(az, sc.c.as<Fr>(), n * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    if (bz) G16_CUDA(cudaMemcpyAsync(bz, sc.c.as<Fr>() + n, n * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    if (cz) G16_CUDA(cudaMemcpyAsync(cz, sc.c.as<Fr>() + 2 * n, n * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    G16_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+int g16_ctx_create(const g16_zkey_view* zkey, int shard_index, int shard_count, g16_ctx** out) {
+  return guard([&] {
+    G16_REQUIRE(zkey != nullptr && out != nullptr, "null argument");
+    std::unique_ptr<g16_ctx> c(new g16_ctx());
+    c->prover.reset(new Prover(*zkey, shard_index, shard_count));
+    *out = c.release();
+  });
+}
+void g16_ctx_destroy(g16_ctx* ctx) { delete ctx; }
+
+static void prove_common(g16_ctx* ctx, const void* witness, int form, int mem_kind, const uint64_t r[4],
+                         const uint64_t s[4], g16_proof* proof, g16_stats* stats) {
+  G16_REQUIRE(ctx && ctx->prover, "context is null");
+  G16_REQUIRE(ctx->prover->shard_count() == 1, "g16_prove needs an unsharded context; use g16_prove_partials");
+  G16_REQUIRE(proof != nullptr, "proof output is null");
+  uint64_t l0 = g_launches.load();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  Prover& p = *ctx->prover;
+  p.start_mask(r, s);
+  p.load_witness(witness, form, mem_kind);
+  p.run_msms(stats);
+  p.finish(proof, stats);
+  if (stats) stats->kernel_launches = (uint32_t)(g_launches.load() - l0);
+}
+
+int g16_prove(g16_ctx* ctx, const uint64_t* witness, int witness_form, const uint64_t r_std[4],
+              const uint64_t s_std[4], g16_proof* proof, g16_stats* stats) {
+  return guard([&] { prove_common(ctx, witness, witness_form, G16_MEM_HOST, r_std, s_std, proof, stats); });
+}
+int g16_prove_dev(g16_ctx* ctx, const void* witness_std_dev, const uint64_t r_std[4], const uint64_t s_std[4],
+                  g16_proof* proof, g16_stats* stats) {
+  return guard([&] { prove_common(ctx, witness_std_dev, G16_FORM_STD, G16_MEM_DEVICE, r_std, s_std, proof, stats); });
+}
+
+int g16_prove_partials(g16_ctx* ctx, const uint64_t* witness, int witness_form, int witness_mem_kind,
+                       void* partials_dev, g16_stats* stats) {
+  return guard([&] {
+    G16_REQUIRE(ctx && ctx->prover, "context is null");
+    G16_REQUIRE(partials_dev != nullptr, "partials buffer is null");
+    uint64_t l0 = g_launches.load();
+    if (stats) memset(stats, 0, sizeof(*stats));
+    Prover& p = *ctx->prover;
+    p.load_witness(witness, witness_form, witness_mem_kind);
+    p.run_msms(stats);
+    p.partials_to_affine(partials_dev);
+    if (stats) stats->kernel_launches = (uint32_t)(g_launches.load() - l0);
+  });
+}
+
+int g16_prove_finish(g16_ctx* ctx, const void* gathered_partials_dev, int count, const uint64_t r_std[4],
+                     const uint64_t s_std[4], g16_proof* proof) {
+  return guard([&] {
+    G16_REQUIRE(ctx && ctx->prover, "context is null");
+    G16_REQUIRE(gathered_partials_dev != nullptr, "partials buffer is null");
+    Prover& p = *ctx->prover;
+    p.start_mask(r_std, s_std);
+    p.sum_partials(gathered_partials_dev, count);
+    p.finish(proof, nullptr);
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+int g16_msm_plan_create(int g2, size_t max_n, int window_bits, g16_msm_plan** out) {
+  return guard([&] {
+    G16_REQUIRE(out != nullptr, "null argument");
+    G16_REQUIRE(window_bits == 0 || (window_bits >= 2 && window_bits <= 22), "window must be 0 (auto) or 2..22");
+    std::unique_ptr<g16_msm_plan> p(new g16_msm_plan());
+    p->g2 = g2 ? 1 : 0;
+    p->window = window_bits;
+    p->max_n = max_n;
+    *out = p.release();
+  });
+}
+void g16_msm_plan_destroy(g16_msm_plan* plan) { delete plan; }
+
+int g16_msm_dev(g16_msm_plan* plan, const void* scalars_dev, int scalar_form, const void* points_dev, size_t n,
+                void* result_xyzz_dev, void* stream) {
+  return guard([&] {
+    G16_REQUIRE(plan != nullptr && result_xyzz_dev != nullptr, "null argument");
+    G16_REQUIRE(scalar_form == G16_FORM_MONT || scalar_form == G16_FORM_STD, "unknown scalar form");
+    MsmConfig cfg;
+    cfg.c = plan->window;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (plan->g2)
+      plan->m2.run(reinterpret_cast<const Fr*>(scalars_dev), scalar_form == G16_FORM_MONT,
+                   reinterpret_cast<const G2Affine*>(points_dev), n, reinterpret_cast<G2XYZZ*>(result_xyzz_dev), s, cfg);
+    else
+      plan->m1.run(reinterpret_cast<const Fr*>(scalars_dev), scalar_form == G16_FORM_MONT,
+                   reinterpret_cast<const G1Affine*>(points_dev), n, reinterpret_cast<G1XYZZ*>(result_xyzz_dev), s, cfg);
+  });
+}
+
+int g16_msm_result_to_affine(int g2, const void* result_xyzz_dev, int count, uint64_t* out_host) {
+  return guard([&] {
+    G16_REQUIRE(result_xyzz_dev && out_host && count >= 1, "bad argument");
+    Scratch& sc = scratch();
+    cudaStream_t s = sc.s();
+    sc.res.ensure(sizeof(G2XYZZ) + sizeof(G2Affine));
+    G16_CUDA(cudaDeviceSynchronize());
+    if (g2) {
+      G2Affine* ra = sc.res.as<G2Affine>();
+      xyzz_sum_to_affine<Fp2>(reinterpret_cast<const G2XYZZ*>(result_xyzz_dev), count, ra, s);
+      G16_CUDA(cudaMemcpyAsync(out_host, ra, sizeof(G2Affine), cudaMemcpyDeviceToHost, s));
+    } else {
+      G1Affine* ra = sc.res.as<G1Affine>();
+      xyzz_sum_to_affine<Fp>(reinterpret_cast<const G1XYZZ*>(result_xyzz_dev), count, ra, s);
+      G16_CUDA(cudaMemcpyAsync(out_host, ra, sizeof(G1Affine), cudaMemcpyDeviceToHost, s));
+    }
+    G16_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int g16_msm_plan_info(const g16_msm_plan* plan, int* window_bits, int* num_windows, size_t* workspace_bytes) {
+  return guard([&] {
+    G16_REQUIRE(plan != nullptr, "null argument");
+    if (window_bits) *window_bits = plan->g2 ? plan->m2.last_c : plan->m1.last_c;
+    if (num_windows) *num_windows = plan->g2 ? plan->m2.last_nwin : plan->m1.last_nwin;
+    if (workspace_bytes) *workspace_bytes = plan->g2 ? plan->m2.workspace_bytes() : plan->m1.workspace_bytes();
+  });
+}
+
+int g16_ntt_prepare(int log_n) {
+  return guard([&] {
+    Scratch& sc = scratch();
+    ntt_prepare(log_n, sc.s());
+  });
+}
+int g16_ntt_fr_dev(const void* in_dev, void* out_dev, void* work_dev, int log_n, int inverse, void* stream) {
+  return guard([&] {
+    G16_REQUIRE(in_dev && out_dev && work_dev, "null argument");
+    G16_REQUIRE(log_n >= 1 && log_n <= 26, "domain must be 2^1 .. 2^26");
+    ntt_natural(reinterpret_cast<const Fr*>(in_dev), reinterpret_cast<Fr*>(out_dev), reinterpret_cast<Fr*>(work_dev),
+                log_n, inverse != 0, reinterpret_cast<cudaStream_t>(stream));
+  });
+}
+int g16_quotient_dev(void* abc_dev, void* qs_dev, int log_n, int flavour, void* stream) {
+  return guard([&] {
+    G16_REQUIRE(abc_dev && qs_dev, "null argument");
+    G16_REQUIRE(log_n >= 1 && log_n <= 26, "domain must be 2^1 .. 2^26");
+    G16_REQUIRE(flavour == G16_FLAVOUR_JENSGROTH || flavour == G16_FLAVOUR_SNARKJS, "unknown flavour");
+    quotient(reinterpret_cast<Fr*>(abc_dev), reinterpret_cast<Fr*>(qs_dev), log_n, flavour,
+             reinterpret_cast<cudaStream_t>(stream));
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+int g16_fake_setup(const g16_r1cs_view* r1cs, const g16_toxic* toxic, uint32_t* log_domain_out, g16_setup_out* out) {
+  return guard([&] {
+    G16_REQUIRE(r1cs && toxic && out, "null argument");
+    fake_setup(*r1cs, *toxic, log_domain_out, *out);
+  });
+}
+
+int g16_fixed_base_g1(const uint64_t* scalars_std, size_t n, uint64_t* points_out) {
+  return guard([&] { fixed_base_host<Fp>(scalars_std, n, points_out); });
+}
+int g16_fixed_base_g2(const uint64_t* scalars_std, size_t n, uint64_t* points_out) {
+  return guard([&] { fixed_base_host<Fp2>(scalars_std, n, points_out); });
+}
+
+int g16_selftest(uint32_t seed, uint32_t cases) {
+  int rc = -1;
+  int st = guard([&] { rc = selftest_run(seed, cases); });
+  if (st != G16_OK) return st;
+  return rc;
+}
+int g16_bench_int_pipe(int kind, double* ops_per_sec, float* ms) {
+  return guard([&] {
+    G16_REQUIRE(kind >= 0 && kind <= 3 && ops_per_sec && ms, "bad argument");
+    bench_int_pipe(kind, ops_per_sec, ms);
+  });
+}
+
+}  // extern "C"

@@ -29,7 +29,13 @@ struct Error : public std::runtime_error {
     if (!(cond)) throw g16::Error(1, std::string(msg)); \
   } while (0)
 
-#define G16_LAUNCH_CHECK() G16_CUDA(cudaGetLastError())
+// every kernel launch of the library is followed by exactly one G16_LAUNCH_CHECK()
+void count_launch();   // capi.cu
+#define G16_LAUNCH_CHECK()       \
+  do {                           \
+    g16::count_launch();         \
+    G16_CUDA(cudaGetLastError()); \
+  } while (0)
 
 // RAII device allocation (grow-only reuse through ensure()).
 struct DevBuf {

@@ -8,6 +8,12 @@
 #pragma once
 #include "field.cuh"
 
+#if defined(__CUDACC__)
+#define G16_NI __host__ __device__ __noinline__
+#else
+#define G16_NI inline
+#endif
+
 namespace g16 {
 
 template <class F>
@@ -110,6 +116,13 @@ G16_HD XYZZ<F> xyzz_dbl(const XYZZ<F>& p) {
   return r;
 }
 
+// Out-of-line copies for cold paths (rare doubling branches, reductions, scalar-mul loops): keeps
+// the hot loops small and the compile time / register pressure of the Fp2 kernels in check.
+template <class F>
+G16_NI void xyzz_dbl_affine_ni(XYZZ<F>& r, const Affine<F>& p) { r = xyzz_dbl_affine(p); }
+template <class F>
+G16_NI void xyzz_dbl_ni(XYZZ<F>& r, const XYZZ<F>& p) { r = xyzz_dbl(p); }
+
 // acc + (affine q)   [madd-2008-s: 8M + 2S], all special cases handled
 template <class F>
 G16_HD XYZZ<F> xyzz_madd(const XYZZ<F>& acc, const Affine<F>& q) {
@@ -120,8 +133,9 @@ G16_HD XYZZ<F> xyzz_madd(const XYZZ<F>& acc, const Affine<F>& q) {
   F Pv = fsub(U2, acc.x);
   F Rv = fsub(S2, acc.y);
   if (fis_zero(Pv)) {
-    if (fis_zero(Rv)) return xyzz_dbl_affine(q);
-    return xyzz_inf<F>();
+    XYZZ<F> d = xyzz_inf<F>();
+    if (fis_zero(Rv)) xyzz_dbl_affine_ni(d, q);
+    return d;
   }
   F PP = fsqr(Pv);
   F PPP = fmul(Pv, PP);
@@ -146,8 +160,9 @@ G16_HD XYZZ<F> xyzz_add(const XYZZ<F>& p, const XYZZ<F>& q) {
   F Pv = fsub(U2, U1);
   F Rv = fsub(S2, S1);
   if (fis_zero(Pv)) {
-    if (fis_zero(Rv)) return xyzz_dbl(p);
-    return xyzz_inf<F>();
+    XYZZ<F> d = xyzz_inf<F>();
+    if (fis_zero(Rv)) xyzz_dbl_ni(d, p);
+    return d;
   }
   F PP = fsqr(Pv);
   F PPP = fmul(Pv, PP);
@@ -160,6 +175,11 @@ G16_HD XYZZ<F> xyzz_add(const XYZZ<F>& p, const XYZZ<F>& q) {
   return r;
 }
 
+template <class F>
+G16_NI void xyzz_add_ni(XYZZ<F>& r, const XYZZ<F>& p, const XYZZ<F>& q) { r = xyzz_add(p, q); }
+template <class F>
+G16_NI void xyzz_madd_ni(XYZZ<F>& r, const XYZZ<F>& p, const Affine<F>& q) { r = xyzz_madd(p, q); }
+
 // XYZZ -> affine, infinity -> (0,0)   (msm.nim:54 prj.affine; curves.nim:49-50)
 template <class F>
 G16_HD Affine<F> xyzz_to_affine(const XYZZ<F>& p) {
@@ -171,6 +191,9 @@ G16_HD Affine<F> xyzz_to_affine(const XYZZ<F>& p) {
   return r;
 }
 
+template <class F>
+G16_NI void xyzz_to_affine_ni(Affine<F>& r, const XYZZ<F>& p) { r = xyzz_to_affine(p); }
+
 // k * P for a standard-form (non-Montgomery) 256-bit scalar, MSB-first double-and-add.
 // (curves.nim:182-196 `**`; used for the six mask terms of prover.nim:279-300.)
 template <class F>
@@ -180,8 +203,8 @@ G16_HD XYZZ<F> xyzz_scalar_mul(const uint32_t k[8], const Affine<F>& p) {
   while (top >= 0 && !((k[top >> 5] >> (top & 31)) & 1u)) top--;
 #pragma unroll 1
   for (int i = top; i >= 0; i--) {
-    acc = xyzz_dbl(acc);
-    if ((k[i >> 5] >> (i & 31)) & 1u) acc = xyzz_madd(acc, p);
+    xyzz_dbl_ni(acc, acc);
+    if ((k[i >> 5] >> (i & 31)) & 1u) xyzz_madd_ni(acc, acc, p);
   }
   return acc;
 }
@@ -195,8 +218,8 @@ G16_HD XYZZ<F> xyzz_mul_u32(uint32_t k, const XYZZ<F>& p) {
   while (!((k >> top) & 1u)) top--;
 #pragma unroll 1
   for (int i = top; i >= 0; i--) {
-    acc = xyzz_dbl(acc);
-    if ((k >> i) & 1u) acc = xyzz_add(acc, p);
+    xyzz_dbl_ni(acc, acc);
+    if ((k >> i) & 1u) xyzz_add_ni(acc, acc, p);
   }
   return acc;
 }

@@ -397,7 +397,12 @@ G16_HD Fe<P> from_mont(const Fe<P>& a) {
 
 // a^(p-2) (Fermat); a = 0 -> 0.  Not unrolled: it is used once per MSM / proof, not per element.
 template <class P>
-G16_HD Fe<P> finv(const Fe<P>& a) {
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+Fe<P> finv(const Fe<P>& a) {
   uint32_t e[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) e[i] = P::mod(i);

@@ -1,0 +1,355 @@
+// Fr NTT and quotient kernels for sm_100a.
+//
+// Replaces groth16/math/ntt.nim:55-77 (forwardNTT), :139-161 (inverseNTT), groth16/math/domain.nim:28-46
+// (createDomain) and the quotient procs groth16/prover.nim:96-113 (multiplyByPowers, shiftEvalDomain),
+// :118-148 (computeQuotientPointwise) and :158-181 (computeSnarkjsScalarCoeffs).
+//
+// Design (DESIGN.md "NTT"): multi-pass radix-2^k transform, each pass running k butterfly stages on a
+// 64 KiB shared-memory tile (limb-major, bank-conflict-free); inverse transforms are
+// decimation-in-frequency (natural in, bit-reversed out), forward transforms inside the quotient are
+// decimation-in-time (bit-reversed in, natural out), so shiftEvalDomain needs no permutation pass:
+// the coset factor eta^i / n is applied, indexed by bit-reversal, in the last inverse pass.
+#include <cuda_runtime.h>
+#include <map>
+#include <memory>
+#include <mutex>
+#include "common.cuh"
+#include "field.cuh"
+#include "ntt.cuh"
+#include "ntt_plan.cuh"
+
+namespace g16 {
+
+// ---------------------------------------------------------------------------------------
+// domain constants and tables
+// ---------------------------------------------------------------------------------------
+// gen28 (domain.nim:26), standard form, little-endian limbs
+__device__ __constant__ uint32_t c_gen28[8] = {0x725b19f0u, 0x9bd61b6eu, 0x41112ed4u, 0x402d111eu,
+                                               0x8ef62abcu, 0x00e0a7ebu, 0xa58a7e85u, 0x2a3c09f0u};
+
+// consts[0]=omega_n  [1]=omega_n^-1  [2]=1/n  [3]=eta=omega_2n  [4]=eta^-1  [5]=1/(eta^n-1)  [6]=1  [7]=omega_n*... spare
+__global__ void k_domain_consts(int log_n, Fr* consts) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Fr g;
+#pragma unroll
+  for (int i = 0; i < 8; i++) g.v[i] = c_gen28[i];
+  g = to_mont(g);
+  Fr eta = g;                                   // omega_{2n} = gen28^(2^(28-log_n-1))   (prover.nim:127,163)
+  for (int i = 0; i < 28 - log_n - 1; i++) eta = fsqr(eta);
+  Fr omega = fsqr(eta);                         // domain.nim:32-33
+  Fr nn = Fr::zero();
+  nn.v[0] = 1u << log_n;
+  consts[0] = omega;
+  consts[1] = finv(omega);                      // domain.nim:43
+  consts[2] = finv(to_mont(nn));                // domain.nim:44
+  consts[3] = eta;
+  consts[4] = finv(eta);
+  Fr etan = eta;
+  for (int i = 0; i < log_n; i++) etan = fsqr(etan);
+  consts[5] = finv(fsub(etan, Fr::one()));      // prover.nim:128 invZ1
+  consts[6] = Fr::one();
+  consts[7] = Fr::zero();
+}
+
+// out[j] = scale * base^j for j < count; each thread produces 8 consecutive powers.
+__global__ void k_gen_powers(Fr* out, uint32_t count, const Fr* base_p, const Fr* scale_p) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t j0 = t * 8u;
+  if (j0 >= count) return;
+  Fr base = *base_p;
+  Fr x = fmul(fpow_u64(base, j0), *scale_p);
+  for (uint32_t j = j0; j < j0 + 8u && j < count; j++) {
+    out[j] = x;
+    x = fmul(x, base);
+  }
+}
+
+struct NttTables {
+  int log_n = -1;
+  DevBuf consts;      // 8 Fr
+  DevBuf tw_fwd;      // omega^j,   j < n/2
+  DevBuf tw_inv;      // omega^-j,  j < n/2
+  DevBuf coset;       // eta^j / n, j < n      (prover.nim:96-106 fused with the 1/n of ntt.nim:139)
+  DevBuf coset_inv;   // eta^-j / n, j < n     (prover.nim:143 fused with 1/n), built lazily
+  bool have_coset_inv = false;
+};
+
+static std::mutex g_tab_mutex;
+static std::map<std::pair<int, int>, std::unique_ptr<NttTables>> g_tables;   // (device, log_n)
+
+static NttTables& ntt_tables(int log_n, cudaStream_t stream) {
+  G16_REQUIRE(log_n >= 1 && log_n <= 26, "NTT domain must be 2^1 .. 2^26");
+  int dev = 0;
+  G16_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_tab_mutex);
+  auto key = std::make_pair(dev, log_n);
+  auto it = g_tables.find(key);
+  if (it != g_tables.end()) return *it->second;
+  std::unique_ptr<NttTables> t(new NttTables());
+  t->log_n = log_n;
+  size_t n = (size_t)1 << log_n;
+  t->consts.ensure(8 * sizeof(Fr));
+  t->tw_fwd.ensure((n / 2) * sizeof(Fr));
+  t->tw_inv.ensure((n / 2) * sizeof(Fr));
+  t->coset.ensure(n * sizeof(Fr));
+  Fr* c = t->consts.as<Fr>();
+  k_domain_consts<<<1, 32, 0, stream>>>(log_n, c);
+  G16_LAUNCH_CHECK();
+  uint32_t half = (uint32_t)(n / 2);
+  k_gen_powers<<<div_up(div_up(half, 8), 128), 128, 0, stream>>>(t->tw_fwd.as<Fr>(), half, c + 0, c + 6);
+  G16_LAUNCH_CHECK();
+  k_gen_powers<<<div_up(div_up(half, 8), 128), 128, 0, stream>>>(t->tw_inv.as<Fr>(), half, c + 1, c + 6);
+  G16_LAUNCH_CHECK();
+  k_gen_powers<<<div_up(div_up(n, 8), 128), 128, 0, stream>>>(t->coset.as<Fr>(), (uint32_t)n, c + 3, c + 2);
+  G16_LAUNCH_CHECK();
+  G16_CUDA(cudaStreamSynchronize(stream));
+  NttTables& ref = *t;
+  g_tables[key] = std::move(t);
+  return ref;
+}
+
+static void ntt_ensure_coset_inv(NttTables& t, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(g_tab_mutex);
+  if (t.have_coset_inv) return;
+  size_t n = (size_t)1 << t.log_n;
+  t.coset_inv.ensure(n * sizeof(Fr));
+  Fr* c = t.consts.as<Fr>();
+  k_gen_powers<<<div_up(div_up(n, 8), 128), 128, 0, stream>>>(t.coset_inv.as<Fr>(), (uint32_t)n, c + 4, c + 2);
+  G16_LAUNCH_CHECK();
+  G16_CUDA(cudaStreamSynchronize(stream));
+  t.have_coset_inv = true;
+}
+
+void ntt_release_tables() {
+  std::lock_guard<std::mutex> lock(g_tab_mutex);
+  g_tables.clear();
+}
+
+// ---------------------------------------------------------------------------------------
+// the pass kernel
+// ---------------------------------------------------------------------------------------
+enum { SC_NONE = 0, SC_CONST = 1, SC_TABLE_BITREV = 2 };
+
+struct NttPassArgs {
+  const Fr* src;        // batch b reads src + b * src_stride
+  Fr* dst;              // batch b writes dst + b * dst_stride (dst == src for in-place passes)
+  size_t src_stride, dst_stride;
+  const Fr* tw;         // n/2 powers of the root for this direction
+  const Fr* scale;      // SC_CONST: one element; SC_TABLE_BITREV: n elements
+  int log_n, t_lo, k, logC;
+  int scale_mode;
+  int bitrev_store;     // store element g at dst[bitrev(g)]
+};
+
+constexpr int NTT_THREADS = 256;
+
+__device__ __forceinline__ Fr ld_fr(const Fr* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ Fr ldg_fr(const Fr* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void st_fr(Fr* p, const Fr& r) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// shared-memory tile, limb-major: limb l of element p at sm[l * E + p]
+__device__ __forceinline__ Fr sm_get(const uint32_t* sm, uint32_t E, uint32_t p) {
+  Fr r;
+#pragma unroll
+  for (int l = 0; l < 8; l++) r.v[l] = sm[l * E + p];
+  return r;
+}
+__device__ __forceinline__ void sm_put(uint32_t* sm, uint32_t E, uint32_t p, const Fr& r) {
+#pragma unroll
+  for (int l = 0; l < 8; l++) sm[l * E + p] = r.v[l];
+}
+
+template <bool DIF>
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs a) {
+  extern __shared__ uint32_t sm[];
+  const uint32_t E = 1u << (a.k + a.logC);
+  const uint32_t tile = blockIdx.x;
+  const Fr* src = a.src + (size_t)blockIdx.y * a.src_stride;
+  Fr* dst = a.dst + (size_t)blockIdx.y * a.dst_stride;
+
+  for (uint32_t p = threadIdx.x; p < E; p += NTT_THREADS) {
+    uint32_t g = ntt_global_index(tile, p, a.t_lo, a.k, a.logC);
+    sm_put(sm, E, p, ld_fr(src + g));
+  }
+  __syncthreads();
+
+  for (int it = 0; it < a.k; it++) {
+    const int s = DIF ? (a.k - 1 - it) : it;
+    const bool trivial = (a.t_lo + s) == 0;           // all twiddles are omega^0
+    for (uint32_t q = threadIdx.x; q < E / 2; q += NTT_THREADS) {
+      uint32_t pu, pv, e;
+      ntt_butterfly_index(tile, q, s, a.t_lo, a.logC, a.log_n, pu, pv, e);
+      Fr u = sm_get(sm, E, pu);
+      Fr v = sm_get(sm, E, pv);
+      if (DIF) {
+        Fr d = fsub(u, v);
+        if (!trivial) d = fmul(d, ldg_fr(a.tw + e));
+        sm_put(sm, E, pu, fadd(u, v));
+        sm_put(sm, E, pv, d);
+      } else {
+        if (!trivial) v = fmul(v, ldg_fr(a.tw + e));
+        sm_put(sm, E, pu, fadd(u, v));
+        sm_put(sm, E, pv, fsub(u, v));
+      }
+    }
+    __syncthreads();
+  }
+
+  for (uint32_t p = threadIdx.x; p < E; p += NTT_THREADS) {
+    uint32_t g = ntt_global_index(tile, p, a.t_lo, a.k, a.logC);
+    Fr x = sm_get(sm, E, p);
+    uint32_t gr = __brev(g) >> (32 - a.log_n);
+    if (a.scale_mode == SC_CONST) x = fmul(x, ldg_fr(a.scale));
+    else if (a.scale_mode == SC_TABLE_BITREV) x = fmul(x, ldg_fr(a.scale + gr));
+    st_fr(dst + (a.bitrev_store ? gr : g), x);
+  }
+}
+
+static void launch_pass(bool dif, const NttPassArgs& a, int batch, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    G16_CUDA(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    G16_CUDA(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  size_t E = (size_t)1 << (a.k + a.logC);
+  size_t tiles = ((size_t)1 << a.log_n) / E;
+  dim3 grid((unsigned)tiles, (unsigned)batch);
+  size_t smem = E * sizeof(Fr);
+  if (dif) k_ntt_pass<true><<<grid, NTT_THREADS, smem, stream>>>(a);
+  else k_ntt_pass<false><<<grid, NTT_THREADS, smem, stream>>>(a);
+  G16_LAUNCH_CHECK();
+}
+
+// Decimation in frequency over all bits: natural-order input, bit-reversed output order.
+// The last pass can scale (SC_*) and/or store to bit-reversed addresses (=> natural order in dst).
+static void run_dif(const Fr* src, Fr* work, Fr* dst, size_t stride, size_t dst_stride, int batch, int log_n,
+                    const Fr* tw, int scale_mode, const Fr* scale, bool bitrev_store, cudaStream_t stream) {
+  NttPlan pl = ntt_make_plan(log_n);
+  for (int i = pl.npass - 1; i >= 0; i--) {
+    bool first = (i == pl.npass - 1), last = (i == 0);
+    NttPassArgs a;
+    a.src = first ? src : work;
+    a.dst = last ? dst : work;
+    a.src_stride = stride;
+    a.dst_stride = last ? dst_stride : stride;
+    a.tw = tw;
+    a.scale = scale;
+    a.log_n = log_n;
+    a.t_lo = pl.pass[i].t_lo;
+    a.k = pl.pass[i].k;
+    a.logC = pl.pass[i].logC;
+    a.scale_mode = last ? scale_mode : SC_NONE;
+    a.bitrev_store = (last && bitrev_store) ? 1 : 0;
+    launch_pass(true, a, batch, stream);
+  }
+}
+
+// Decimation in time over all bits: bit-reversed input order, natural-order output; in place.
+static void run_dit(Fr* data, size_t stride, int batch, int log_n, const Fr* tw, cudaStream_t stream) {
+  NttPlan pl = ntt_make_plan(log_n);
+  for (int i = 0; i < pl.npass; i++) {
+    NttPassArgs a;
+    a.src = data;
+    a.dst = data;
+    a.src_stride = a.dst_stride = stride;
+    a.tw = tw;
+    a.scale = nullptr;
+    a.log_n = log_n;
+    a.t_lo = pl.pass[i].t_lo;
+    a.k = pl.pass[i].k;
+    a.logC = pl.pass[i].logC;
+    a.scale_mode = SC_NONE;
+    a.bitrev_store = 0;
+    launch_pass(false, a, batch, stream);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// element-wise kernels
+// ---------------------------------------------------------------------------------------
+__global__ void k_pointwise_mul(const Fr* a, const Fr* b, Fr* c, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    st_fr(c + i, fmul(ld_fr(a + i), ld_fr(b + i)));
+}
+
+// out = a*b - c   (prover.nim:176), optionally * invZ (prover.nim:141)
+__global__ void k_quotient_pointwise(const Fr* a, const Fr* b, const Fr* c, Fr* out, uint32_t n, const Fr* invz) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Fr x = fsub(fmul(ld_fr(a + i), ld_fr(b + i)), ld_fr(c + i));
+    if (invz) x = fmul(x, ldg_fr(invz));
+    st_fr(out + i, x);
+  }
+}
+
+static unsigned ew_grid(size_t n) {
+  size_t g = (n + 255) / 256;
+  size_t cap = 148 * 16;
+  return (unsigned)(g < cap ? (g ? g : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------
+// public (library-internal) entry points
+// ---------------------------------------------------------------------------------------
+void ntt_prepare(int log_n, cudaStream_t stream) { (void)ntt_tables(log_n, stream); }
+
+void ntt_natural(const Fr* in, Fr* out, Fr* work, int log_n, bool inverse, cudaStream_t stream) {
+  G16_REQUIRE(in != out && work != out, "ntt_natural: output must not alias input/work");
+  NttTables& t = ntt_tables(log_n, stream);
+  size_t n = (size_t)1 << log_n;
+  if (inverse)
+    run_dif(in, work, out, n, n, 1, log_n, t.tw_inv.as<Fr>(), SC_CONST, t.consts.as<Fr>() + 2, true, stream);
+  else
+    run_dif(in, work, out, n, n, 1, log_n, t.tw_fwd.as<Fr>(), SC_NONE, nullptr, true, stream);
+}
+
+// abc: 3n elements [Az | Bz | scratch]; on return abc is clobbered and qs holds the n scalars that
+// multiply the H points.  flavour: 0 = JensGroth (prover.nim:118-148), 1 = Snarkjs (prover.nim:158-181).
+void quotient(Fr* abc, Fr* qs, int log_n, int flavour, cudaStream_t stream) {
+  G16_REQUIRE(log_n >= 1, "quotient: the reference needs a domain of at least 2 (prover.nim:101)");
+  NttTables& t = ntt_tables(log_n, stream);
+  size_t n = (size_t)1 << log_n;
+  Fr* A = abc;
+  Fr* B = abc + n;
+  Fr* C = abc + 2 * n;
+  k_pointwise_mul<<<ew_grid(n), 256, 0, stream>>>(A, B, C, (uint32_t)n);        // prover.nim:69-71
+  G16_LAUNCH_CHECK();
+  // shiftEvalDomain (prover.nim:109-113) on the three vectors at once
+  run_dif(abc, abc, abc, n, n, 3, log_n, t.tw_inv.as<Fr>(), SC_TABLE_BITREV, t.coset.as<Fr>(), false, stream);
+  run_dit(abc, n, 3, log_n, t.tw_fwd.as<Fr>(), stream);
+  if (flavour == 1) {
+    k_quotient_pointwise<<<ew_grid(n), 256, 0, stream>>>(A, B, C, qs, (uint32_t)n, nullptr);
+    G16_LAUNCH_CHECK();
+  } else {
+    ntt_ensure_coset_inv(t, stream);
+    k_quotient_pointwise<<<ew_grid(n), 256, 0, stream>>>(A, B, C, A, (uint32_t)n, t.consts.as<Fr>() + 5);
+    G16_LAUNCH_CHECK();
+    // inverse NTT (prover.nim:142) then * eta^-i (prover.nim:143), natural order out
+    run_dif(A, A, qs, n, n, 1, log_n, t.tw_inv.as<Fr>(), SC_TABLE_BITREV, t.coset_inv.as<Fr>(), true, stream);
+  }
+}
+
+void pointwise_mul(const Fr* a, const Fr* b, Fr* c, size_t n, cudaStream_t stream) {
+  k_pointwise_mul<<<ew_grid(n), 256, 0, stream>>>(a, b, c, (uint32_t)n);
+  G16_LAUNCH_CHECK();
+}
+
+}  // namespace g16

@@ -1,0 +1,348 @@
+// Resident Groth16 proving context on one B200.
+//
+// Replaces generateProofWithMask (groth16/prover.nim:215-304): buildABC (:245), the quotient (:250-260),
+// the five MSMs (:279-302) and the proof assembly (:278-304).  The zkey's prover points and its
+// coefficient list are uploaded once (g16_ctx_create); per proof only the witness travels.  The five
+// MSMs are independent given the witness (A1, B1, B2, C1) and the quotient (H1), so they run on five
+// streams; the mask terms that need no MSM result (r*delta1, s*delta1, s*delta2, -rs*delta1) run on a
+// sixth.  A context may own only the point range [N*k/G, N*(k+1)/G) of every MSM (msm.nim:107-115): then
+// run_msms() yields partial sums that the host side all-gathers between GPUs.
+#include "prover.cuh"
+#include "ntt.cuh"
+
+namespace g16 {
+
+template <class T>
+static __device__ __forceinline__ T ldv(const T* p) {
+  T r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = q[i];
+  return r;
+}
+template <class T>
+static __device__ __forceinline__ void stv(T* p, const T& v) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) q[i] = s[i];
+}
+
+// -(r*s) mod the group order, standard form in and out
+static __device__ void neg_rs(const uint32_t r[8], const uint32_t s[8], uint32_t out[8]) {
+  Fr a, b;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a.v[i] = r[i];
+    b.v[i] = s[i];
+  }
+  Fr p = fneg(fmul(to_mont(a), to_mont(b)));   // prover.nim:300 negFr(r*s)
+  p = from_mont(p);
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[i] = p.v[i];
+}
+
+// mask terms that do not depend on any MSM; warps 0..3 work independently (lane 0 only)
+__global__ void __launch_bounds__(128) k_mask_terms(const SpecPointsDev* spec, MaskTerms* m) {
+  if (threadIdx.x & 31) return;
+  int w = threadIdx.x >> 5;
+  if (w == 0) {                                       // alpha1 + r ** delta1      prover.nim:280-281
+    G1XYZZ t = xyzz_scalar_mul(m->r, ldv(&spec->delta1));
+    xyzz_madd_ni(t, t, ldv(&spec->alpha1));
+    stv(&m->t_a, t);
+  } else if (w == 1) {                                // beta1 + s ** delta1       prover.nim:286-287
+    G1XYZZ t = xyzz_scalar_mul(m->s, ldv(&spec->delta1));
+    xyzz_madd_ni(t, t, ldv(&spec->beta1));
+    stv(&m->t_b1, t);
+  } else if (w == 2) {                                // beta2 + s ** delta2       prover.nim:292-293
+    G2XYZZ t = xyzz_scalar_mul(m->s, ldv(&spec->delta2));
+    xyzz_madd_ni(t, t, ldv(&spec->beta2));
+    stv(&m->t_b2, t);
+  } else {                                            // negFr(r*s) ** delta1      prover.nim:300
+    uint32_t k[8];
+    neg_rs(m->r, m->s, k);
+    G1XYZZ t = xyzz_scalar_mul(k, ldv(&spec->delta1));
+    stv(&m->t_c, t);
+  }
+}
+
+// proof assembly, prover.nim:278-304
+__global__ void __launch_bounds__(128) k_assemble(const MsmResults* res, const MaskTerms* m, g16_proof* proof) {
+  __shared__ G1XYZZ sh[3];
+  int w = threadIdx.x >> 5;
+  bool lead = (threadIdx.x & 31) == 0;
+  if (lead) {
+    if (w == 0) {                                     // pi_a, then s ** pi_a       prover.nim:282,298
+      G1XYZZ t;
+      xyzz_add_ni(t, ldv(&m->t_a), ldv(&res->a1));
+      G1Affine pa;
+      xyzz_to_affine_ni(pa, t);
+      stv(reinterpret_cast<G1Affine*>(proof->pi_a), pa);
+      sh[0] = xyzz_scalar_mul(m->s, pa);
+    } else if (w == 1) {                              // rho, then r ** rho         prover.nim:288,299
+      G1XYZZ t;
+      xyzz_add_ni(t, ldv(&m->t_b1), ldv(&res->b1));
+      G1Affine rho;
+      xyzz_to_affine_ni(rho, t);
+      sh[1] = xyzz_scalar_mul(m->r, rho);
+    } else if (w == 2) {                              // pi_b                       prover.nim:294
+      G2XYZZ t;
+      xyzz_add_ni(t, ldv(&m->t_b2), ldv(&res->b2));
+      G2Affine pb;
+      xyzz_to_affine_ni(pb, t);
+      stv(reinterpret_cast<G2Affine*>(proof->pi_b), pb);
+    } else {                                          // -rs*delta1 + MSM(H) + MSM(C)   prover.nim:300-302
+      G1XYZZ t;
+      xyzz_add_ni(t, ldv(&m->t_c), ldv(&res->h1));
+      xyzz_add_ni(t, t, ldv(&res->c1));
+      sh[2] = t;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    G1XYZZ t;
+    xyzz_add_ni(t, sh[0], sh[1]);
+    xyzz_add_ni(t, t, sh[2]);
+    G1Affine pc;
+    xyzz_to_affine_ni(pc, t);
+    stv(reinterpret_cast<G1Affine*>(proof->pi_c), pc);
+  }
+}
+
+// XYZZ results -> affine partial sums (the per-chunk prj.affine of msm.nim:54,81)
+__global__ void __launch_bounds__(160) k_partials_to_affine(const MsmResults* res, PartialsAffine* out) {
+  if (threadIdx.x & 31) return;
+  int w = threadIdx.x >> 5;
+  if (w < 4) {
+    const G1XYZZ* src = w == 0 ? &res->a1 : w == 1 ? &res->b1 : w == 2 ? &res->h1 : &res->c1;
+    G1Affine* dst = w == 0 ? &out->a1 : w == 1 ? &out->b1 : w == 2 ? &out->h1 : &out->c1;
+    G1Affine a;
+    xyzz_to_affine_ni(a, ldv(src));
+    stv(dst, a);
+  } else {
+    G2Affine a;
+    xyzz_to_affine_ni(a, ldv(&res->b2));
+    stv(&out->b2, a);
+  }
+}
+
+// gathered affine partial sums -> XYZZ totals (res += sync pending[k], msm.nim:117-119)
+__global__ void __launch_bounds__(160) k_sum_partials(const PartialsAffine* parts, int count, MsmResults* res) {
+  if (threadIdx.x & 31) return;
+  int w = threadIdx.x >> 5;
+  if (w < 4) {
+    G1XYZZ acc = xyzz_inf<Fp>();
+    for (int i = 0; i < count; i++) {
+      const PartialsAffine* p = parts + i;
+      const G1Affine* src = w == 0 ? &p->a1 : w == 1 ? &p->b1 : w == 2 ? &p->h1 : &p->c1;
+      xyzz_madd_ni(acc, acc, ldv(src));
+    }
+    G1XYZZ* dst = w == 0 ? &res->a1 : w == 1 ? &res->b1 : w == 2 ? &res->h1 : &res->c1;
+    stv(dst, acc);
+  } else {
+    G2XYZZ acc = xyzz_inf<Fp2>();
+    for (int i = 0; i < count; i++) xyzz_madd_ni(acc, acc, ldv(&parts[i].b2));
+    stv(&res->b2, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+static void shard_range(size_t N, int k, int G, size_t& lo, size_t& hi) {   // msm.nim:107-111
+  lo = (N * (size_t)k) / (size_t)G;
+  hi = (k == G - 1) ? N : (N * (size_t)(k + 1)) / (size_t)G;
+}
+
+static void upload(DevBuf& dst, const void* src, size_t elem, size_t lo, size_t hi, int mem_kind) {
+  size_t bytes = (hi - lo) * elem;
+  dst.ensure(bytes ? bytes : 16);
+  if (!bytes) return;
+  G16_REQUIRE(src != nullptr, "zkey view: missing point array");
+  const char* s = reinterpret_cast<const char*>(src) + lo * elem;
+  G16_CUDA(cudaMemcpy(dst.p, s, bytes, mem_kind == G16_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+}
+
+Prover::Prover(const g16_zkey_view& zk, int shard_index, int shard_count)
+    : shard_index_(shard_index), shard_count_(shard_count) {
+  G16_REQUIRE(shard_count >= 1 && shard_index >= 0 && shard_index < shard_count, "bad shard index/count");
+  G16_REQUIRE(zk.log_domain >= 1 && zk.log_domain <= 26, "domain size must be 2^1 .. 2^26 (prover.nim:101)");
+  G16_REQUIRE(zk.flavour == G16_FLAVOUR_JENSGROTH || zk.flavour == G16_FLAVOUR_SNARKJS, "unknown flavour");
+  G16_REQUIRE(zk.nvars >= zk.npubs + 1, "nvars must be at least npubs + 1");
+  nvars_ = zk.nvars;
+  npubs_ = zk.npubs;
+  log_n_ = zk.log_domain;
+  flavour_ = zk.flavour;
+  n_ = (size_t)1 << log_n_;
+  for (int i = 0; i < 24; i++) ev_[i] = nullptr;
+
+  shard_range(nvars_, shard_index, shard_count, v_lo_, v_hi_);
+  shard_range((size_t)nvars_ - npubs_ - 1, shard_index, shard_count, c_lo_, c_hi_);
+  shard_range(n_, shard_index, shard_count, h_lo_, h_hi_);
+  upload(ptsA1_, zk.points_a1, sizeof(G1Affine), v_lo_, v_hi_, zk.mem_kind);
+  upload(ptsB1_, zk.points_b1, sizeof(G1Affine), v_lo_, v_hi_, zk.mem_kind);
+  upload(ptsB2_, zk.points_b2, sizeof(G2Affine), v_lo_, v_hi_, zk.mem_kind);
+  upload(ptsC1_, zk.points_c1, sizeof(G1Affine), c_lo_, c_hi_, zk.mem_kind);
+  upload(ptsH1_, zk.points_h1, sizeof(G1Affine), h_lo_, h_hi_, zk.mem_kind);
+
+  G16_CUDA(cudaStreamCreateWithFlags(&main_, cudaStreamNonBlocking));
+  for (int i = 0; i < 5; i++) G16_CUDA(cudaStreamCreateWithFlags(&st_[i], cudaStreamNonBlocking));
+  G16_CUDA(cudaStreamCreateWithFlags(&st_mask_, cudaStreamNonBlocking));
+  for (int i = 0; i < 24; i++) G16_CUDA(cudaEventCreate(&ev_[i]));
+
+  // coefficient list -> CSR rows (once per zkey)
+  {
+    size_t rec = zk.coeff_format == G16_COEFF_PACKED44_R2 ? 44 : 48;
+    DevBuf raw;
+    raw.ensure(zk.ncoeffs * rec + 16);
+    if (zk.ncoeffs) {
+      G16_REQUIRE(zk.coeffs != nullptr, "zkey view: missing coefficient list");
+      G16_CUDA(cudaMemcpy(raw.p, zk.coeffs, zk.ncoeffs * rec,
+                          zk.mem_kind == G16_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    }
+    coeffs_to_csr(csr_, raw.p, zk.ncoeffs, (int)zk.coeff_format, (int)log_n_, nvars_, main_);
+  }
+
+  SpecPointsDev sp;
+  memcpy(&sp.alpha1, zk.alpha1, 64);
+  memcpy(&sp.beta1, zk.beta1, 64);
+  memcpy(&sp.delta1, zk.delta1, 64);
+  memcpy(&sp.beta2, zk.beta2, 128);
+  memcpy(&sp.delta2, zk.delta2, 128);
+  spec_.ensure(sizeof(SpecPointsDev));
+  G16_CUDA(cudaMemcpy(spec_.p, &sp, sizeof(sp), cudaMemcpyHostToDevice));
+
+  witness_.ensure((size_t)nvars_ * sizeof(Fr));
+  abc_.ensure(3 * n_ * sizeof(Fr));
+  qs_.ensure(n_ * sizeof(Fr));
+  results_.ensure(sizeof(MsmResults));
+  mask_.ensure(sizeof(MaskTerms));
+  proof_.ensure(sizeof(g16_proof));
+  G16_CUDA(cudaMallocHost(reinterpret_cast<void**>(&proof_pinned_), sizeof(g16_proof)));
+  ntt_prepare((int)log_n_, main_);
+  G16_CUDA(cudaStreamSynchronize(main_));
+}
+
+Prover::~Prover() {
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 24; i++)
+    if (ev_[i]) cudaEventDestroy(ev_[i]);
+  for (int i = 0; i < 5; i++)
+    if (st_[i]) cudaStreamDestroy(st_[i]);
+  if (st_mask_) cudaStreamDestroy(st_mask_);
+  if (main_) cudaStreamDestroy(main_);
+  if (proof_pinned_) cudaFreeHost(proof_pinned_);
+}
+
+void Prover::sync() { G16_CUDA(cudaStreamSynchronize(main_)); }
+
+void Prover::load_witness(const void* w, int form, int mem_kind) {
+  G16_REQUIRE(w != nullptr, "witness is null");
+  G16_REQUIRE(form == G16_FORM_MONT || form == G16_FORM_STD, "unknown witness form");
+  size_t bytes = (size_t)nvars_ * sizeof(Fr);
+  cudaMemcpyKind kind = mem_kind == G16_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  G16_CUDA(cudaEventRecord(ev_[20], main_));
+  if (form == G16_FORM_STD) {
+    G16_CUDA(cudaMemcpyAsync(witness_.p, w, bytes, kind, main_));
+  } else {
+    staging_.ensure(bytes);
+    G16_CUDA(cudaMemcpyAsync(staging_.p, w, bytes, kind, main_));
+    fr_from_mont(staging_.as<Fr>(), witness_.as<Fr>(), nvars_, main_);
+  }
+  G16_CUDA(cudaEventRecord(ev_[21], main_));
+}
+
+void Prover::run_msms(g16_stats* stats) {
+  // ev_[0]: witness ready on main_; every worker stream waits for it
+  G16_CUDA(cudaEventRecord(ev_[0], main_));
+  for (int i = 0; i < 5; i++) G16_CUDA(cudaStreamWaitEvent(st_[i], ev_[0], 0));
+  MsmResults* res = results_.as<MsmResults>();
+  const Fr* w = witness_.as<Fr>();
+
+  // stream 0: ABC -> quotient -> MSM over the H points   (prover.nim:245-260, 301)
+  G16_CUDA(cudaEventRecord(ev_[1], st_[0]));
+  build_abc(csr_, w, abc_.as<Fr>(), (int)log_n_, st_[0]);
+  G16_CUDA(cudaEventRecord(ev_[2], st_[0]));
+  quotient(abc_.as<Fr>(), qs_.as<Fr>(), (int)log_n_, (int)flavour_, st_[0]);
+  G16_CUDA(cudaEventRecord(ev_[3], st_[0]));
+  msmH_.run(qs_.as<Fr>() + h_lo_, true, ptsH1_.as<G1Affine>(), h_hi_ - h_lo_, &res->h1, st_[0]);
+  G16_CUDA(cudaEventRecord(ev_[4], st_[0]));
+  // stream 1: pi_A MSM (prover.nim:282)
+  G16_CUDA(cudaEventRecord(ev_[5], st_[1]));
+  msmA_.run(w + v_lo_, false, ptsA1_.as<G1Affine>(), v_hi_ - v_lo_, &res->a1, st_[1]);
+  G16_CUDA(cudaEventRecord(ev_[6], st_[1]));
+  // stream 2: rho MSM (prover.nim:288)
+  G16_CUDA(cudaEventRecord(ev_[7], st_[2]));
+  msmB1_.run(w + v_lo_, false, ptsB1_.as<G1Affine>(), v_hi_ - v_lo_, &res->b1, st_[2]);
+  G16_CUDA(cudaEventRecord(ev_[8], st_[2]));
+  // stream 3: pi_B MSM in G2 (prover.nim:294)
+  G16_CUDA(cudaEventRecord(ev_[9], st_[3]));
+  msmB2_.run(w + v_lo_, false, ptsB2_.as<G2Affine>(), v_hi_ - v_lo_, &res->b2, st_[3]);
+  G16_CUDA(cudaEventRecord(ev_[10], st_[3]));
+  // stream 4: MSM over the C points with zs = witness[npubs+1 ..] (prover.nim:262-264, 302)
+  G16_CUDA(cudaEventRecord(ev_[11], st_[4]));
+  msmC_.run(w + npubs_ + 1 + c_lo_, false, ptsC1_.as<G1Affine>(), c_hi_ - c_lo_, &res->c1, st_[4]);
+  G16_CUDA(cudaEventRecord(ev_[12], st_[4]));
+
+  for (int i = 0; i < 5; i++) {
+    G16_CUDA(cudaEventRecord(ev_[13 + i], st_[i]));
+    G16_CUDA(cudaStreamWaitEvent(main_, ev_[13 + i], 0));
+  }
+  G16_CUDA(cudaEventRecord(ev_[18], main_));
+  if (stats) {
+    G16_CUDA(cudaStreamSynchronize(main_));
+    cudaEventElapsedTime(&stats->ms_abc, ev_[1], ev_[2]);
+    cudaEventElapsedTime(&stats->ms_quotient, ev_[2], ev_[3]);
+    cudaEventElapsedTime(&stats->ms_msm_h, ev_[3], ev_[4]);
+    cudaEventElapsedTime(&stats->ms_msm_a, ev_[5], ev_[6]);
+    cudaEventElapsedTime(&stats->ms_msm_b1, ev_[7], ev_[8]);
+    cudaEventElapsedTime(&stats->ms_msm_b2, ev_[9], ev_[10]);
+    cudaEventElapsedTime(&stats->ms_msm_c, ev_[11], ev_[12]);
+    cudaEventElapsedTime(&stats->ms_h2d, ev_[20], ev_[21]);
+  }
+}
+
+void Prover::partials_to_affine(void* partials_dev) {
+  k_partials_to_affine<<<1, 160, 0, main_>>>(results_.as<MsmResults>(), reinterpret_cast<PartialsAffine*>(partials_dev));
+  G16_LAUNCH_CHECK();
+  G16_CUDA(cudaStreamSynchronize(main_));
+}
+
+void Prover::sum_partials(const void* gathered_dev, int count) {
+  G16_REQUIRE(count >= 1, "need at least one partial record");
+  k_sum_partials<<<1, 160, 0, main_>>>(reinterpret_cast<const PartialsAffine*>(gathered_dev), count,
+                                       results_.as<MsmResults>());
+  G16_LAUNCH_CHECK();
+}
+
+// r*delta1, s*delta1, s*delta2, -rs*delta1 need no MSM result: started early on their own stream
+void Prover::start_mask(const uint64_t r[4], const uint64_t s[4]) {
+  G16_REQUIRE(r != nullptr && s != nullptr, "mask is null");
+  MaskTerms* m = mask_.as<MaskTerms>();
+  uint32_t rs[16];
+  memcpy(rs, r, 32);
+  memcpy(rs + 8, s, 32);
+  G16_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(m) + offsetof(MaskTerms, r), rs, 64, cudaMemcpyHostToDevice,
+                           st_mask_));
+  k_mask_terms<<<1, 128, 0, st_mask_>>>(spec_.as<SpecPointsDev>(), m);
+  G16_LAUNCH_CHECK();
+  G16_CUDA(cudaEventRecord(ev_[23], st_mask_));
+}
+
+void Prover::finish(g16_proof* proof, g16_stats* stats) {
+  G16_REQUIRE(proof != nullptr, "proof output is null");
+  MaskTerms* m = mask_.as<MaskTerms>();
+  G16_CUDA(cudaEventRecord(ev_[19], main_));
+  G16_CUDA(cudaStreamWaitEvent(main_, ev_[23], 0));
+  k_assemble<<<1, 128, 0, main_>>>(results_.as<MsmResults>(), m, proof_.as<g16_proof>());
+  G16_LAUNCH_CHECK();
+  G16_CUDA(cudaMemcpyAsync(proof_pinned_, proof_.p, sizeof(g16_proof), cudaMemcpyDeviceToHost, main_));
+  G16_CUDA(cudaEventRecord(ev_[22], main_));
+  G16_CUDA(cudaStreamSynchronize(main_));
+  memcpy(proof, proof_pinned_, sizeof(g16_proof));
+  if (stats) {
+    cudaEventElapsedTime(&stats->ms_assemble, ev_[19], ev_[22]);
+    cudaEventElapsedTime(&stats->ms_total, ev_[20], ev_[22]);
+  }
+}
+
+}  // namespace g16

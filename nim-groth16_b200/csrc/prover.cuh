@@ -1,0 +1,68 @@
+// Library-internal interface of prover.cu: the resident proving context.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/g16b200.h"
+#include "abc.cuh"
+#include "common.cuh"
+#include "ec.cuh"
+#include "msm.cuh"
+
+namespace g16 {
+
+struct alignas(16) PartialsAffine {   // == g16_partials
+  G1Affine a1, b1, h1, c1;
+  G2Affine b2;
+};
+static_assert(sizeof(PartialsAffine) == sizeof(g16_partials), "g16_partials layout");
+
+struct alignas(16) MsmResults {       // XYZZ sums of the five MSMs
+  G1XYZZ a1, b1, h1, c1;
+  G2XYZZ b2;
+};
+
+struct alignas(16) MaskTerms {        // prover.nim:279-300, everything that does not depend on an MSM
+  G1XYZZ t_a;    // alpha1 + r * delta1
+  G1XYZZ t_b1;   // beta1 + s * delta1
+  G1XYZZ t_c;    // (-r*s) * delta1
+  G2XYZZ t_b2;   // beta2 + s * delta2
+  uint32_t r[8], s[8];
+};
+
+struct alignas(16) SpecPointsDev {    // SpecPoints (zkey_types.nim:24-31) needed by the prover
+  G1Affine alpha1, beta1, delta1;
+  G2Affine beta2, delta2;
+};
+
+class Prover {
+ public:
+  Prover(const g16_zkey_view& zk, int shard_index, int shard_count);
+  ~Prover();
+  // witness upload (host or device source) into the resident standard-form buffer
+  void load_witness(const void* w, int form, int mem_kind);
+  void run_msms(g16_stats* stats);                     // ABC, quotient, five MSMs -> results_
+  void partials_to_affine(void* partials_dev);         // results_ -> g16_partials (device)
+  void sum_partials(const void* gathered_dev, int count);   // gathered g16_partials -> results_
+  void start_mask(const uint64_t r[4], const uint64_t s[4]);   // mask terms on their own stream
+  void finish(g16_proof* proof, g16_stats* stats);             // assemble (waits for start_mask)
+  int shard_count() const { return shard_count_; }
+  uint32_t nvars() const { return nvars_; }
+  Fr* witness_dev() { return witness_.as<Fr>(); }
+  void sync();
+
+ private:
+  int shard_index_, shard_count_;
+  uint32_t nvars_, npubs_, log_n_, flavour_;
+  size_t n_;
+  size_t v_lo_, v_hi_, c_lo_, c_hi_, h_lo_, h_hi_;
+  DevBuf ptsA1_, ptsB1_, ptsB2_, ptsC1_, ptsH1_;
+  SparseCsr csr_;
+  DevBuf spec_, witness_, staging_, abc_, qs_, results_, mask_, proof_;
+  Msm<Fp> msmA_, msmB1_, msmH_, msmC_;
+  Msm<Fp2> msmB2_;
+  cudaStream_t main_ = nullptr, st_mask_ = nullptr, st_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_[24];
+  g16_proof* proof_pinned_ = nullptr;
+  float ms_h2d_ = 0.f;
+};
+
+}  // namespace g16

@@ -1,0 +1,60 @@
+"""Multi-GPU proving: one process per GPU (torch.distributed), each owning a contiguous point range of
+every MSM -- the chunking of msm.nim:107-115 lifted from CPU threads to devices.  The only exchange
+is an all-gather of one 384-byte record of partial sums per rank (msm.nim:117-119)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .encoding import FORM_STD
+from .prover import MEM_DEVICE, MEM_HOST, ProverContext
+from .zkey_types import Mask, Proof, ZKey
+
+
+def shard_range(n: int, k: int, g: int):
+    """[N*k/G, N*(k+1)/G) with the last shard taking the remainder (msm.nim:107-111)."""
+    lo = (n * k) // g
+    hi = n if k == g - 1 else (n * (k + 1)) // g
+    return lo, hi
+
+
+def gather_partials(local: "torch.Tensor", group=None) -> "torch.Tensor":   # noqa: F821
+    """All-gather of the per-rank partial-sum records (uint8[384]) -> uint8[world, 384]."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    flat = torch.empty(world * local.numel(), dtype=torch.uint8, device=local.device)
+    dist.all_gather_into_tensor(flat, local.contiguous().view(-1), group=group)
+    return flat.view(world, local.numel())
+
+
+class ShardedProver:
+    """A prover context per rank; prove() returns the full proof on every rank."""
+
+    def __init__(self, zkey: ZKey, rank: int, world: int, device: Optional[int] = None):
+        import torch
+        self.rank, self.world = rank, world
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        _lib.check(_lib.load().g16_set_device(self.device.index))
+        self.ctx = ProverContext(zkey, rank, world)
+        self.partials = torch.zeros(_lib.PARTIALS_BYTES, dtype=torch.uint8, device=self.device)
+
+    def prove_raw(self, witness_ptr: int, mem_kind: int, mask: Mask, group=None):
+        import torch
+        self.ctx.prove_partials(witness_ptr, FORM_STD, mem_kind, self.partials.data_ptr())
+        if self.world > 1:
+            allp = gather_partials(self.partials, group)
+            torch.cuda.current_stream().synchronize()
+        else:
+            allp = self.partials.view(1, -1)
+        return self.ctx.prove_finish(allp.data_ptr(), self.world, mask)
+
+    def prove(self, witness: np.ndarray, mask: Mask, group=None) -> Proof:
+        w = np.ascontiguousarray(witness, dtype=np.uint64).reshape(-1, 4)
+        raw = self.prove_raw(w.ctypes.data, MEM_HOST, mask, group)
+        return self.ctx._proof(raw, w, FORM_STD)
+
+    def close(self):
+        self.ctx.close()

@@ -5,7 +5,95 @@
 #include "field.cuh"
 #include "ec.cuh"
 #include "msm_digits.cuh"
+#include "ntt_plan.cuh"
+#include <vector>
 using namespace g16;
+
+// ---- host emulation of the pass structure of ntt.cu (same index helpers, same stage order) ----
+static Fr gen28_mont() {
+  static const uint32_t g[8] = {0x725b19f0u, 0x9bd61b6eu, 0x41112ed4u, 0x402d111eu,
+                                0x8ef62abcu, 0x00e0a7ebu, 0xa58a7e85u, 0x2a3c09f0u};
+  Fr x;
+  for (int i = 0; i < 8; i++) x.v[i] = g[i];
+  return to_mont(x);
+}
+struct EmuTables {
+  std::vector<Fr> tw_fwd, tw_inv, coset;
+  Fr n_inv;
+};
+static EmuTables emu_tables(int log_n) {
+  EmuTables t;
+  size_t n = (size_t)1 << log_n;
+  Fr eta = gen28_mont();
+  for (int i = 0; i < 28 - log_n - 1; i++) eta = fsqr(eta);
+  Fr omega = fsqr(eta), omega_inv = finv(omega);
+  Fr nn = Fr::zero();
+  nn.v[0] = 1u << log_n;
+  t.n_inv = finv(to_mont(nn));
+  t.tw_fwd.resize(n / 2 ? n / 2 : 1);
+  t.tw_inv.resize(n / 2 ? n / 2 : 1);
+  t.coset.resize(n);
+  Fr a = Fr::one(), b = Fr::one(), c = t.n_inv;
+  for (size_t j = 0; j < n; j++) {
+    if (j < n / 2) { t.tw_fwd[j] = a; t.tw_inv[j] = b; }
+    t.coset[j] = c;
+    a = fmul(a, omega); b = fmul(b, omega_inv); c = fmul(c, eta);
+  }
+  return t;
+}
+// one pass over all tiles; scale_mode 0 none, 1 const, 2 table[bitrev]
+static void emu_pass(bool dif, std::vector<Fr>& src, std::vector<Fr>& dst, const std::vector<Fr>& tw, int log_n,
+                     NttPass ps, int scale_mode, const Fr* scale, bool bitrev_store) {
+  uint32_t E = 1u << (ps.k + ps.logC);
+  uint32_t tiles = (1u << log_n) / E;
+  std::vector<Fr> out(dst.size());
+  bool alias = (&src == &dst);
+  for (uint32_t tile = 0; tile < tiles; tile++) {
+    std::vector<Fr> sm(E);
+    for (uint32_t p = 0; p < E; p++) sm[p] = src[ntt_global_index(tile, p, ps.t_lo, ps.k, ps.logC)];
+    for (int it = 0; it < ps.k; it++) {
+      int s = dif ? (ps.k - 1 - it) : it;
+      bool trivial = (ps.t_lo + s) == 0;
+      for (uint32_t q = 0; q < E / 2; q++) {
+        uint32_t pu, pv, e;
+        ntt_butterfly_index(tile, q, s, ps.t_lo, ps.logC, log_n, pu, pv, e);
+        Fr u = sm[pu], v = sm[pv];
+        if (dif) {
+          Fr d = fsub(u, v);
+          if (!trivial) d = fmul(d, tw[e]);
+          sm[pu] = fadd(u, v);
+          sm[pv] = d;
+        } else {
+          if (!trivial) v = fmul(v, tw[e]);
+          sm[pu] = fadd(u, v);
+          sm[pv] = fsub(u, v);
+        }
+      }
+    }
+    for (uint32_t p = 0; p < E; p++) {
+      uint32_t g = ntt_global_index(tile, p, ps.t_lo, ps.k, ps.logC);
+      uint32_t gr = ntt_bitrev(g, log_n);
+      Fr x = sm[p];
+      if (scale_mode == 1) x = fmul(x, *scale);
+      else if (scale_mode == 2) x = fmul(x, scale[gr]);
+      (alias ? out : dst)[bitrev_store ? gr : g] = x;
+    }
+  }
+  if (alias) dst = out;
+}
+static void emu_dif(std::vector<Fr>& v, std::vector<Fr>& dst, const std::vector<Fr>& tw, int log_n, int scale_mode,
+                    const Fr* scale, bool bitrev_store) {
+  NttPlan pl = ntt_make_plan(log_n);
+  for (int i = pl.npass - 1; i >= 0; i--) {
+    bool last = (i == 0);
+    if (last) emu_pass(true, v, dst, tw, log_n, pl.pass[i], scale_mode, scale, bitrev_store);
+    else emu_pass(true, v, v, tw, log_n, pl.pass[i], 0, nullptr, false);
+  }
+}
+static void emu_dit(std::vector<Fr>& v, const std::vector<Fr>& tw, int log_n) {
+  NttPlan pl = ntt_make_plan(log_n);
+  for (int i = 0; i < pl.npass; i++) emu_pass(false, v, v, tw, log_n, pl.pass[i], 0, nullptr, false);
+}
 
 extern "C" {
 void he_fr_mul(const uint32_t* a, const uint32_t* b, uint32_t* c) { *(Fr*)c = fmul(*(const Fr*)a, *(const Fr*)b); }
@@ -68,5 +156,23 @@ void he_g1_mul_u32(uint32_t k, const uint32_t* p, uint32_t* out) {
 // signed-digit decomposition used by the MSM (msm_digits.cuh)
 void he_digits(const uint32_t* k, int c, int nwin, int* out) {
   for (int w = 0, carry = 0; w < nwin; w++) out[w] = msm_signed_digit(k, c, w, nwin, carry);
+}
+// natural-order NTT as ntt_natural() in ntt.cu
+void he_ntt(const uint32_t* in, uint32_t* out, int log_n, int inverse) {
+  size_t n = (size_t)1 << log_n;
+  EmuTables t = emu_tables(log_n);
+  std::vector<Fr> v((const Fr*)in, (const Fr*)in + n), dst(n);
+  if (inverse) emu_dif(v, dst, t.tw_inv, log_n, 1, &t.n_inv, true);
+  else emu_dif(v, dst, t.tw_fwd, log_n, 0, nullptr, true);
+  memcpy(out, dst.data(), n * sizeof(Fr));
+}
+// shiftEvalDomain as quotient() in ntt.cu: DIF inverse with coset[bitrev] scaling, then DIT forward
+void he_shift_eval(const uint32_t* in, uint32_t* out, int log_n) {
+  size_t n = (size_t)1 << log_n;
+  EmuTables t = emu_tables(log_n);
+  std::vector<Fr> v((const Fr*)in, (const Fr*)in + n);
+  emu_dif(v, v, t.tw_inv, log_n, 2, t.coset.data(), false);
+  emu_dit(v, t.tw_fwd, log_n);
+  memcpy(out, v.data(), n * sizeof(Fr));
 }
 }

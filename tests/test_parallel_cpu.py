@@ -1,0 +1,74 @@
+"""CPU (gloo, world_size 2): the host-side plumbing of the multi-GPU split -- shard ranges follow the
+reference's chunking (msm.nim:107-111) and the partial-sum records all-gather intact and in rank order."""
+import os
+import socket
+
+import pytest
+
+import g16_oracle as o
+
+
+def test_shard_ranges_match_reference_chunking():
+    from g16b200.parallel import shard_range
+    for n in (0, 1, 7, 128, 1000, (1 << 20) + 3):
+        for g in (1, 2, 3, 4, 8):
+            a = 0
+            for k in range(g):
+                lo, hi = shard_range(n, k, g)
+                b = (n * (k + 1)) // g if k < g - 1 else n           # msm.nim:107-111
+                assert (lo, hi) == (a, b)
+                a = b
+            assert a == n
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from g16b200.parallel import gather_partials
+    local = torch.full((384,), rank + 1, dtype=torch.uint8)
+    local[0] = 7 * (rank + 1)
+    out = gather_partials(local)
+    q.put((rank, out.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_partials_world2_gloo():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        rows = res[rank]
+        assert len(rows) == 2 and rows[0][0] == 7 and rows[1][0] == 14
+        assert rows[0][1:] == [1] * 383 and rows[1][1:] == [2] * 383
+
+
+def test_sharded_partial_sums_recombine_in_the_oracle():
+    """msm.nim:117-119: the sum of per-shard MSMs equals the whole MSM (what prove_finish relies on)."""
+    import random
+    from g16b200.parallel import shard_range
+    rnd = random.Random(1)
+    n = 37
+    ks = [rnd.randrange(o.R) for _ in range(n)]
+    pts = [o.g1_mul(rnd.randrange(1, 1 << 40), o.GEN1) for _ in range(n)]
+    whole = o.msm_naive_g1(ks, pts)
+    for g in (2, 4):
+        acc = o.INF_G1
+        for k in range(g):
+            lo, hi = shard_range(n, k, g)
+            acc = o.g1_add(acc, o.msm_naive_g1(ks[lo:hi], pts[lo:hi]))
+        assert acc == whole
