@@ -174,6 +174,12 @@ int g16_msm_dev(g16_msm_plan* plan, const void* scalars_dev, int scalar_form, co
                 void* result_xyzz_dev, void* stream);
 int g16_msm_result_to_affine(int g2, const void* result_xyzz_dev, int count, uint64_t* out_host);
 int g16_msm_plan_info(const g16_msm_plan* plan, int* window_bits, int* num_windows, size_t* workspace_bytes);
+/* per-kernel timing of the dominant kernel (bucket accumulation) with CUDA events on the launch stream */
+int g16_msm_plan_profile(g16_msm_plan* plan, int enable);
+int g16_msm_plan_last_profile(const g16_msm_plan* plan, float* accumulate_ms, float* total_ms, uint64_t* pairs);
+/* device timer on the context's main stream: brackets every kernel and copy issued for the context */
+int g16_ctx_timer_start(g16_ctx* ctx);
+int g16_ctx_timer_stop(g16_ctx* ctx, float* elapsed_ms);
 
 /* in_dev/out_dev/work_dev: 2^log_n elements each (out distinct from the others) */
 int g16_ntt_fr_dev(const void* in_dev, void* out_dev, void* work_dev, int log_n, int inverse, void* stream);

@@ -352,6 +352,33 @@ int g16_msm_plan_info(const g16_msm_plan* plan, int* window_bits, int* num_windo
   });
 }
 
+int g16_msm_plan_profile(g16_msm_plan* plan, int enable) {
+  return guard([&] {
+    G16_REQUIRE(plan != nullptr, "null argument");
+    plan->m1.profile = plan->m2.profile = (enable != 0);
+  });
+}
+int g16_msm_plan_last_profile(const g16_msm_plan* plan, float* accumulate_ms, float* total_ms, uint64_t* pairs) {
+  return guard([&] {
+    G16_REQUIRE(plan != nullptr, "null argument");
+    if (accumulate_ms) *accumulate_ms = plan->g2 ? plan->m2.last_accum_ms() : plan->m1.last_accum_ms();
+    if (total_ms) *total_ms = plan->g2 ? plan->m2.last_total_ms() : plan->m1.last_total_ms();
+    if (pairs) *pairs = plan->g2 ? plan->m2.last_pairs : plan->m1.last_pairs;
+  });
+}
+int g16_ctx_timer_start(g16_ctx* ctx) {
+  return guard([&] {
+    G16_REQUIRE(ctx && ctx->prover, "context is null");
+    ctx->prover->timer_start();
+  });
+}
+int g16_ctx_timer_stop(g16_ctx* ctx, float* elapsed_ms) {
+  return guard([&] {
+    G16_REQUIRE(ctx && ctx->prover && elapsed_ms, "null argument");
+    *elapsed_ms = ctx->prover->timer_stop();
+  });
+}
+
 int g16_ntt_prepare(int log_n) {
   return guard([&] {
     Scratch& sc = scratch();

@@ -24,9 +24,17 @@ class Msm {
   // device memory currently held by the workspace
   size_t workspace_bytes() const;
   int last_c = 0, last_nwin = 0;
+  // optional per-kernel timing of the dominant kernel (bucket accumulation), CUDA events on `stream`
+  bool profile = false;
+  float last_accum_ms() const;     // valid after the stream has been synchronised
+  float last_total_ms() const;
+  uint64_t last_pairs = 0;         // non-zero (scalar, window) digits of the last run (filled when profiling)
+  ~Msm();
 
  private:
   DevBuf keys_[2], vals_[2], start_, buckets_, winpart_, cub_tmp_;
+  cudaEvent_t pev_[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint32_t nbuckets_last_ = 0;
 };
 
 // parts[0..count) summed and normalised to affine (infinity -> (0,0)); one tiny kernel.

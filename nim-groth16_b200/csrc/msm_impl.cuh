@@ -212,6 +212,24 @@ size_t Msm<F>::workspace_bytes() const {
 }
 
 template <class F>
+Msm<F>::~Msm() {
+  for (int i = 0; i < 4; i++)
+    if (pev_[i]) cudaEventDestroy(pev_[i]);
+}
+template <class F>
+float Msm<F>::last_accum_ms() const {
+  float ms = 0.f;
+  if (pev_[1] && pev_[2]) cudaEventElapsedTime(&ms, pev_[1], pev_[2]);
+  return ms;
+}
+template <class F>
+float Msm<F>::last_total_ms() const {
+  float ms = 0.f;
+  if (pev_[0] && pev_[3]) cudaEventElapsedTime(&ms, pev_[0], pev_[3]);
+  return ms;
+}
+
+template <class F>
 void Msm<F>::run(const Fr* scalars, bool scalars_mont, const Affine<F>* points, size_t n, XYZZ<F>* result,
                  cudaStream_t stream, const MsmConfig& cfg) {
   G16_REQUIRE(n < ((size_t)1 << 31), "MSM size must be below 2^31");
@@ -229,6 +247,11 @@ void Msm<F>::run(const Fr* scalars, bool scalars_mont, const Affine<F>* points, 
   G16_REQUIRE(m < ((size_t)1 << 32), "MSM pair count must fit 32 bits");
   last_c = c;
   last_nwin = nwin;
+  if (profile) {
+    for (int i = 0; i < 4; i++)
+      if (!pev_[i]) G16_CUDA(cudaEventCreate(&pev_[i]));
+    G16_CUDA(cudaEventRecord(pev_[0], stream));
+  }
 
   keys_[0].ensure(m * 4);
   keys_[1].ensure(m * 4);
@@ -262,9 +285,11 @@ void Msm<F>::run(const Fr* scalars, bool scalars_mont, const Affine<F>* points, 
   k_bucket_bounds<<<div_up((size_t)nbuckets + 1, 256), 256, 0, stream>>>(keys_[1].as<uint32_t>(), m, nbuckets,
                                                                          start_.as<uint32_t>());
   G16_LAUNCH_CHECK();
+  if (profile) G16_CUDA(cudaEventRecord(pev_[1], stream));
   k_bucket_accumulate<F><<<div_up(nbuckets, 128), 128, 0, stream>>>(vals_[1].as<uint32_t>(), start_.as<uint32_t>(),
                                                                     points, buckets_.as<XYZZ<F>>(), nbuckets);
   G16_LAUNCH_CHECK();
+  if (profile) G16_CUDA(cudaEventRecord(pev_[2], stream));
   dim3 rgrid(bpw, (unsigned)nwin);
   k_bucket_reduce<F><<<rgrid, tpb, tpb * sizeof(XYZZ<F>), stream>>>(buckets_.as<XYZZ<F>>(), nb, L,
                                                                     winpart_.as<XYZZ<F>>());
@@ -273,6 +298,13 @@ void Msm<F>::run(const Fr* scalars, bool scalars_mont, const Affine<F>* points, 
   k_window_combine<F><<<1, cthreads, (size_t)nwin * sizeof(XYZZ<F>), stream>>>(winpart_.as<XYZZ<F>>(), bpw, nwin, c,
                                                                                result);
   G16_LAUNCH_CHECK();
+  if (profile) {
+    G16_CUDA(cudaEventRecord(pev_[3], stream));
+    uint32_t pairs = 0;   // start[nbuckets] = number of sorted pairs with a real bucket key
+    G16_CUDA(cudaMemcpyAsync(&pairs, start_.as<uint32_t>() + nbuckets, 4, cudaMemcpyDeviceToHost, stream));
+    G16_CUDA(cudaStreamSynchronize(stream));
+    last_pairs = pairs;
+  }
 }
 
 template <class F>

@@ -231,9 +231,25 @@ Prover::~Prover() {
   if (st_mask_) cudaStreamDestroy(st_mask_);
   if (main_) cudaStreamDestroy(main_);
   if (proof_pinned_) cudaFreeHost(proof_pinned_);
+  for (int i = 0; i < 2; i++)
+    if (tev_[i]) cudaEventDestroy(tev_[i]);
 }
 
 void Prover::sync() { G16_CUDA(cudaStreamSynchronize(main_)); }
+
+void Prover::timer_start() {
+  for (int i = 0; i < 2; i++)
+    if (!tev_[i]) G16_CUDA(cudaEventCreate(&tev_[i]));
+  G16_CUDA(cudaEventRecord(tev_[0], main_));
+}
+float Prover::timer_stop() {
+  G16_REQUIRE(tev_[0] && tev_[1], "timer_stop without timer_start");
+  G16_CUDA(cudaEventRecord(tev_[1], main_));
+  G16_CUDA(cudaEventSynchronize(tev_[1]));
+  float ms = 0.f;
+  G16_CUDA(cudaEventElapsedTime(&ms, tev_[0], tev_[1]));
+  return ms;
+}
 
 void Prover::load_witness(const void* w, int form, int mem_kind) {
   G16_REQUIRE(w != nullptr, "witness is null");

@@ -48,6 +48,8 @@ class Prover {
   uint32_t nvars() const { return nvars_; }
   Fr* witness_dev() { return witness_.as<Fr>(); }
   void sync();
+  void timer_start();                 // CUDA event on the context's main stream
+  float timer_stop();                 // records, synchronises, returns elapsed ms since timer_start()
 
  private:
   int shard_index_, shard_count_;
@@ -61,6 +63,7 @@ class Prover {
   Msm<Fp2> msmB2_;
   cudaStream_t main_ = nullptr, st_mask_ = nullptr, st_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_[24];
+  cudaEvent_t tev_[2] = {nullptr, nullptr};
   g16_proof* proof_pinned_ = nullptr;
   float ms_h2d_ = 0.f;
 };

@@ -82,6 +82,11 @@ SIGNATURES = {
     "g16_msm_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "g16_msm_result_to_affine": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "g16_msm_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "g16_msm_plan_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "g16_msm_plan_last_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                            C.POINTER(C.c_uint64)]),
+    "g16_ctx_timer_start": (C.c_int, [C.c_void_p]),
+    "g16_ctx_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "g16_ntt_fr_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "g16_quotient_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "g16_ntt_prepare": (C.c_int, [C.c_int]),
