@@ -113,15 +113,15 @@ typedef struct g16_proof {            /* Proof (prover.nim:38-43) minus publicIO
   uint64_t pi_c[8];
 } g16_proof;
 
-typedef struct g16_stats {            /* device-side milliseconds under the reference's timing labels */
+typedef struct g16_stats {            /* device-side milliseconds (CUDA events on the launch streams) */
   float ms_h2d;                       /* witness upload */
   float ms_abc;                       /* "building 'ABC'"                    prover.nim:244 */
   float ms_quotient;                  /* "computing the quotient (FFTs)"     prover.nim:249 */
-  float ms_msm_a;                     /* "computing pi_A (G1 MSM)"           prover.nim:279 */
-  float ms_msm_b1;                    /* "computing rho (G1 MSM)"            prover.nim:285 */
+  float ms_sort_witness;              /* digit decomposition + sort shared by the four witness MSMs */
+  float ms_msm_g1_witness;            /* pi_A, rho and the C part of pi_C (A1, B1, C1 fused)  prover.nim:279-288,302 */
   float ms_msm_b2;                    /* "computing pi_B (G2 MSM)"           prover.nim:291 */
-  float ms_msm_h;                     /* "computing pi_C (2x G1 MSM)": H     prover.nim:297 */
-  float ms_msm_c;                     /*                               and C */
+  float ms_msm_h;                     /* the H part of "computing pi_C (2x G1 MSM)" incl. its sort  prover.nim:301 */
+  float reserved_ms;
   float ms_assemble;
   float ms_total;
   uint32_t kernel_launches;           /* launches of this library's own kernels during the call */
@@ -160,6 +160,8 @@ int g16_prove_dev(g16_ctx* ctx, const void* witness_std_dev, const uint64_t r_st
  *   any rank:    g16_prove_finish over the gathered records -> the proof. */
 int g16_prove_partials(g16_ctx* ctx, const uint64_t* witness, int witness_form, int witness_mem_kind,
                        void* partials_dev, g16_stats* stats);
+/* the five MSM sums of the most recent g16_prove* call on this context, as affine records (diagnostics) */
+int g16_ctx_last_partials(g16_ctx* ctx, void* partials_dev);
 int g16_prove_finish(g16_ctx* ctx, const void* gathered_partials_dev, int count, const uint64_t r_std[4],
                      const uint64_t s_std[4], g16_proof* proof);
 
@@ -172,6 +174,11 @@ void g16_msm_plan_destroy(g16_msm_plan* plan);
 /* result_dev: XYZZ accumulator (128 B for G1, 256 B for G2) */
 int g16_msm_dev(g16_msm_plan* plan, const void* scalars_dev, int scalar_form, const void* points_dev, size_t n,
                 void* result_xyzz_dev, void* stream);
+/* Resident-key layout used by g16_ctx: a table of 2^(c*w) * P_i for every window w, built once per point
+ * array (table_dev: ceil(255/c) * n affine points), then MSMs against it share one bucket set. */
+int g16_msm_plan_build_table(g16_msm_plan* plan, const void* points_dev, size_t n, void** table_dev_out);
+int g16_msm_dev_table(g16_msm_plan* plan, const void* scalars_dev, int scalar_form, size_t n, void* result_xyzz_dev,
+                      void* stream);
 int g16_msm_result_to_affine(int g2, const void* result_xyzz_dev, int count, uint64_t* out_host);
 int g16_msm_plan_info(const g16_msm_plan* plan, int* window_bits, int* num_windows, size_t* workspace_bytes);
 /* per-kernel timing of the dominant kernel (bucket accumulation) with CUDA events on the launch stream */

@@ -105,7 +105,7 @@ static void msm_host(Msm<F>& eng, const uint64_t* scalars, int form, const uint6
   }
   XYZZ<F>* r = sc.res.as<XYZZ<F>>();
   Affine<F>* ra = reinterpret_cast<Affine<F>*>(r + 1);
-  eng.run(sc.a.as<Fr>(), form == G16_FORM_MONT, sc.b.as<Affine<F>>(), n, r, s);
+  eng.run(sc.a.as<Fr>(), form == G16_FORM_MONT, sc.b.as<Affine<F>>(), n, r, s, 0);
   xyzz_sum_to_affine<F>(r, 1, ra, s);
   G16_CUDA(cudaMemcpyAsync(out, ra, sizeof(Affine<F>), cudaMemcpyDeviceToHost, s));
   G16_CUDA(cudaStreamSynchronize(s));
@@ -138,6 +138,9 @@ struct g16_msm_plan {
   size_t max_n = 0;
   Msm<Fp> m1;
   Msm<Fp2> m2;
+  DevBuf table;          // resident window table (g16_msm_plan_build_table)
+  size_t table_n = 0;
+  int table_c = 0;
 };
 
 extern "C" {
@@ -280,6 +283,13 @@ int g16_prove_partials(g16_ctx* ctx, const uint64_t* witness, int witness_form, 
   });
 }
 
+int g16_ctx_last_partials(g16_ctx* ctx, void* partials_dev) {
+  return guard([&] {
+    G16_REQUIRE(ctx && ctx->prover && partials_dev, "null argument");
+    ctx->prover->partials_to_affine(partials_dev);
+  });
+}
+
 int g16_prove_finish(g16_ctx* ctx, const void* gathered_partials_dev, int count, const uint64_t r_std[4],
                      const uint64_t s_std[4], g16_proof* proof) {
   return guard([&] {
@@ -311,15 +321,49 @@ int g16_msm_dev(g16_msm_plan* plan, const void* scalars_dev, int scalar_form, co
   return guard([&] {
     G16_REQUIRE(plan != nullptr && result_xyzz_dev != nullptr, "null argument");
     G16_REQUIRE(scalar_form == G16_FORM_MONT || scalar_form == G16_FORM_STD, "unknown scalar form");
-    MsmConfig cfg;
-    cfg.c = plan->window;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (plan->g2)
       plan->m2.run(reinterpret_cast<const Fr*>(scalars_dev), scalar_form == G16_FORM_MONT,
-                   reinterpret_cast<const G2Affine*>(points_dev), n, reinterpret_cast<G2XYZZ*>(result_xyzz_dev), s, cfg);
+                   reinterpret_cast<const G2Affine*>(points_dev), n, reinterpret_cast<G2XYZZ*>(result_xyzz_dev), s,
+                   plan->window);
     else
       plan->m1.run(reinterpret_cast<const Fr*>(scalars_dev), scalar_form == G16_FORM_MONT,
-                   reinterpret_cast<const G1Affine*>(points_dev), n, reinterpret_cast<G1XYZZ*>(result_xyzz_dev), s, cfg);
+                   reinterpret_cast<const G1Affine*>(points_dev), n, reinterpret_cast<G1XYZZ*>(result_xyzz_dev), s,
+                   plan->window);
+  });
+}
+
+int g16_msm_plan_build_table(g16_msm_plan* plan, const void* points_dev, size_t n, void** table_dev_out) {
+  return guard([&] {
+    G16_REQUIRE(plan != nullptr && points_dev != nullptr && n > 0, "bad argument");
+    int c = plan->window ? plan->window : msm_pick_window(n, true);
+    size_t elem = plan->g2 ? sizeof(G2Affine) : sizeof(G1Affine);
+    plan->table.ensure((size_t)msm_num_windows(c) * n * elem);
+    cudaStream_t s = scratch().s();
+    if (plan->g2)
+      msm_build_table<Fp2>(reinterpret_cast<const G2Affine*>(points_dev), n, 0, c, plan->table.as<G2Affine>(), s);
+    else
+      msm_build_table<Fp>(reinterpret_cast<const G1Affine*>(points_dev), n, 0, c, plan->table.as<G1Affine>(), s);
+    G16_CUDA(cudaStreamSynchronize(s));
+    plan->table_n = n;
+    plan->table_c = c;
+    if (table_dev_out) *table_dev_out = plan->table.p;
+  });
+}
+
+int g16_msm_dev_table(g16_msm_plan* plan, const void* scalars_dev, int scalar_form, size_t n, void* result_xyzz_dev,
+                      void* stream) {
+  return guard([&] {
+    G16_REQUIRE(plan != nullptr && result_xyzz_dev != nullptr, "null argument");
+    G16_REQUIRE(plan->table_n == n && n > 0, "no table of this size: call g16_msm_plan_build_table first");
+    G16_REQUIRE(scalar_form == G16_FORM_MONT || scalar_form == G16_FORM_STD, "unknown scalar form");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (plan->g2)
+      plan->m2.run_precomp(reinterpret_cast<const Fr*>(scalars_dev), scalar_form == G16_FORM_MONT,
+                           plan->table.as<G2Affine>(), n, plan->table_c, reinterpret_cast<G2XYZZ*>(result_xyzz_dev), s);
+    else
+      plan->m1.run_precomp(reinterpret_cast<const Fr*>(scalars_dev), scalar_form == G16_FORM_MONT,
+                           plan->table.as<G1Affine>(), n, plan->table_c, reinterpret_cast<G1XYZZ*>(result_xyzz_dev), s);
   });
 }
 
@@ -355,7 +399,8 @@ int g16_msm_plan_info(const g16_msm_plan* plan, int* window_bits, int* num_windo
 int g16_msm_plan_profile(g16_msm_plan* plan, int enable) {
   return guard([&] {
     G16_REQUIRE(plan != nullptr, "null argument");
-    plan->m1.profile = plan->m2.profile = (enable != 0);
+    plan->m1.set_profile(enable != 0);
+    plan->m2.set_profile(enable != 0);
   });
 }
 int g16_msm_plan_last_profile(const g16_msm_plan* plan, float* accumulate_ms, float* total_ms, uint64_t* pairs) {

@@ -110,8 +110,8 @@ int selftest_run(uint32_t seed, uint32_t cases) {
   DevBuf din, dout;
   din.ensure(cases * sizeof(SelfCase));
   dout.ensure(cases * sizeof(SelfOut));
-  G16_CUDA(cudaMemcpy(din.p, in.data(), cases * sizeof(SelfCase), cudaMemcpyHostToDevice));
-  k_selftest<<<div_up(cases, 32), 32>>>(din.as<SelfCase>(), dout.as<SelfOut>(), cases);
+  G16_CUDA(cudaMemcpyAsync(din.p, in.data(), cases * sizeof(SelfCase), cudaMemcpyHostToDevice, 0));
+  k_selftest<<<div_up(cases, 32), 32>>>(din.as<SelfCase>(), dout.as<SelfOut>(), cases);   // same (default) stream
   G16_LAUNCH_CHECK();
   G16_CUDA(cudaDeviceSynchronize());
   std::vector<SelfOut> got(cases);

@@ -1,52 +1,124 @@
-// Library-internal interface of msm.cu: GPU Pippenger over G1 (Fp) and G2 (Fp2).
+// Library-internal interface of the MSM engine: GPU Pippenger over G1 (Fp) and G2 (Fp2).
 // Replaces groth16/bn128/msm.nim:35-59,63-83 (msmConstantineG1/G2 -> constantine multiScalarMul*)
 // and the thread chunking of msm.nim:89-158.
+//
+// Two layers:
+//   MsmSorter        scalars -> signed window digits -> radix sort by bucket -> bucket bounds ->
+//                    length-balanced work items.  Depends only on the scalars, so the four witness MSMs of a
+//                    proof (A1, B1, B2, C1) share one sorter run.
+//   MsmAccumulator   sorted pairs + one point set -> bucket sums -> bucket reduction -> one XYZZ point.
+// Two point layouts:
+//   plain            n affine points; every window has its own 2^(c-1) buckets; Horner over the windows.
+//   precomputed      a table of W*n affine points, table[w*n + i] = 2^(c*w) * P_i, resident in HBM; all
+//                    windows share ONE bucket set, so there is no window combination and c can be larger.
 #pragma once
 #include <cuda_runtime.h>
 #include "common.cuh"
 #include "ec.cuh"
+#include "msm_digits.cuh"
 
 namespace g16 {
 
-struct MsmConfig {
-  int c = 0;          // window bits (0 = pick from n)
+struct MsmGeometry {
+  size_t n = 0;            // scalars / points
+  int c = 0;               // window bits
+  int nwin = 0;            // windows = ceil(255 / c)
+  bool precomp = false;
+  uint32_t nb = 0;         // buckets per window = 2^(c-1)
+  uint32_t nbuckets = 0;   // bucket sets * nb  (precomp: nb; plain: nwin * nb)
+  size_t m = 0;            // (scalar, window) pairs = nwin * n
+  uint32_t T = 0;          // maximum additions per work item
+  uint32_t max_items = 0;  // upper bound on work items
+};
+
+int msm_pick_window(size_t n, bool precomp);
+MsmGeometry msm_geometry(size_t n, int c, bool precomp);
+
+class MsmSorter {
+ public:
+  MsmSorter() {}
+  ~MsmSorter();
+  // scalars: n x 32 bytes on the device; scalars_mont: Montgomery residues (the reference's in-memory Fr,
+  // msm.nim:42-44 toBig) or standard-form integers (.wtns bytes).
+  void run(const Fr* scalars, bool scalars_mont, const MsmGeometry& g, cudaStream_t stream);
+  const MsmGeometry& geom() const { return g_; }
+  size_t workspace_bytes() const;
+  // device views, valid after run() (stream order)
+  const uint32_t* vals() const { return vals_[1].as<uint32_t>(); }
+  const uint32_t* start() const { return start_.as<uint32_t>(); }
+  const uint32_t* item_start() const { return item_start_.as<uint32_t>(); }
+  const uint32_t* item_bucket() const { return item_bucket_.as<uint32_t>(); }
+  const uint32_t* items_sorted() const { return item_idx_[1].as<uint32_t>(); }
+  const uint32_t* multi_list() const { return multi_.as<uint32_t>() + 1; }
+  const uint32_t* multi_count() const { return multi_.as<uint32_t>(); }
+
+ private:
+  MsmGeometry g_;
+  DevBuf keys_[2], vals_[2], start_, chunks_, item_start_, item_bucket_, item_key_[2], item_idx_[2], multi_, cub_tmp_;
 };
 
 template <class F>
+struct MsmPointSet {
+  const Affine<F>* points = nullptr;   // plain: n points; precomputed: nwin * n table
+  XYZZ<F>* result = nullptr;           // device, one XYZZ point
+};
+
+template <class F>
+class MsmAccumulator {
+ public:
+  static constexpr int MAX_SETS = 3;
+  MsmAccumulator() {}
+  ~MsmAccumulator();
+  // up to MAX_SETS point sets over the same sorted pairs, accumulated in the same launches
+  void run(const MsmSorter& sorter, const MsmPointSet<F>* sets, int nsets, cudaStream_t stream);
+  size_t workspace_bytes() const;
+  bool profile = false;                // CUDA events around the accumulate kernel on `stream`
+  float last_accum_ms() const;
+
+ private:
+  DevBuf buckets_, partials_, winpart_;
+  cudaEvent_t pev_[2] = {nullptr, nullptr};
+};
+
+// The reference-shaped single MSM (plain layout): sorter + accumulator.
+template <class F>
 class Msm {
  public:
-  Msm() {}
-  // result (XYZZ, device memory) = sum_i scalars[i] * points[i].
-  // scalars: n x 32 bytes on the device; `scalars_mont` says whether they are Montgomery residues
-  // (the reference's in-memory Fr, msm.nim:42-44 toBig) or standard-form integers (.wtns bytes).
+  // result (XYZZ, device memory) = sum_i scalars[i] * points[i]
   void run(const Fr* scalars, bool scalars_mont, const Affine<F>* points, size_t n, XYZZ<F>* result,
-           cudaStream_t stream, const MsmConfig& cfg = MsmConfig());
-  // device memory currently held by the workspace
-  size_t workspace_bytes() const;
-  int last_c = 0, last_nwin = 0;
-  // optional per-kernel timing of the dominant kernel (bucket accumulation), CUDA events on `stream`
-  bool profile = false;
-  float last_accum_ms() const;     // valid after the stream has been synchronised
+           cudaStream_t stream, int window_bits = 0);
+  // same with a precomputed table built by msm_build_table (window bits fixed by the table)
+  void run_precomp(const Fr* scalars, bool scalars_mont, const Affine<F>* table, size_t n, int window_bits,
+                   XYZZ<F>* result, cudaStream_t stream);
+  size_t workspace_bytes() const { return sorter_.workspace_bytes() + acc_.workspace_bytes(); }
+  void set_profile(bool on) { profile_ = on; acc_.profile = on; }
+  float last_accum_ms() const { return acc_.last_accum_ms(); }
   float last_total_ms() const;
-  uint64_t last_pairs = 0;         // non-zero (scalar, window) digits of the last run (filled when profiling)
+  uint64_t last_pairs = 0;
+  int last_c = 0, last_nwin = 0;
   ~Msm();
 
  private:
-  DevBuf keys_[2], vals_[2], start_, buckets_, winpart_, cub_tmp_;
-  cudaEvent_t pev_[4] = {nullptr, nullptr, nullptr, nullptr};
-  uint32_t nbuckets_last_ = 0;
+  void go(const Fr* scalars, bool mont, const Affine<F>* pts, const MsmGeometry& g, XYZZ<F>* result, cudaStream_t s);
+  MsmSorter sorter_;
+  MsmAccumulator<F> acc_;
+  bool profile_ = false;
+  cudaEvent_t tev_[2] = {nullptr, nullptr};
 };
+
+// table[w * n + i] = 2^(c*w) * points[i] for w < ceil(255/c), affine (infinity stays (0,0)).
+// `pad_front` leading entries of every window are written as infinity (used to align the C1 points with
+// witness indices: prover.nim:262-264 zs = witness[npubs+1 ..]).
+template <class F>
+void msm_build_table(const Affine<F>* points, size_t n_points, size_t pad_front, int c, Affine<F>* table,
+                     cudaStream_t stream);
 
 // parts[0..count) summed and normalised to affine (infinity -> (0,0)); one tiny kernel.
 template <class F>
 void xyzz_sum_to_affine(const XYZZ<F>* parts, int count, Affine<F>* out, cudaStream_t stream);
 
-// affine partial sums (one per shard, msm.nim:117-119) -> XYZZ sum
-template <class F>
-void affine_sum_to_xyzz(const Affine<F>* parts, int count, XYZZ<F>* out, cudaStream_t stream);
-
-int msm_pick_window(size_t n, bool g2);
-
+extern template class MsmAccumulator<Fp>;
+extern template class MsmAccumulator<Fp2>;
 extern template class Msm<Fp>;
 extern template class Msm<Fp2>;
 

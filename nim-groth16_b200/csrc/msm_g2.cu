@@ -1,10 +1,11 @@
-// G2 (Fp2) instantiation of the MSM pipeline; see msm_impl.cuh.
+// G2 (Fp2) instantiation of the MSM back end; see msm_impl.cuh.
 #include "msm_impl.cuh"
 
 namespace g16 {
 
+template class MsmAccumulator<Fp2>;
 template class Msm<Fp2>;
+template void msm_build_table<Fp2>(const Affine<Fp2>*, size_t, size_t, int, Affine<Fp2>*, cudaStream_t);
 template void xyzz_sum_to_affine<Fp2>(const XYZZ<Fp2>*, int, Affine<Fp2>*, cudaStream_t);
-template void affine_sum_to_xyzz<Fp2>(const Affine<Fp2>*, int, XYZZ<Fp2>*, cudaStream_t);
 
 }  // namespace g16

@@ -1,17 +1,16 @@
 // (template implementation, included by msm_g1.cu and msm_g2.cu)
-// GPU Pippenger multi-scalar multiplication for BN254 G1 / G2 on sm_100a.
+// MSM back end on sm_100a: bucket accumulation over length-balanced work items, bucket reduction and the
+// final combination, for up to three point sets sharing one MsmSorter run.
 //
-// Replaces groth16/bn128/msm.nim:35-59 (msmConstantineG1), :63-83 (msmConstantineG2) and the
-// chunk-per-thread driver msm.nim:89-158; the result is the same canonical group element.
+// Replaces the per-chunk Pippenger the reference delegates to constantine (groth16/bn128/msm.nim:49 / :76)
+// and the partial-sum loop of msm.nim:117-119; the result is the same canonical group element.
 //
-// Pipeline (DESIGN.md "MSM"):
-//   1. k_msm_digits        signed-digit windows of each scalar -> (bucket key, point index|sign)
-//   2. radix sort          (key, value) pairs by bucket key (CUB device radix sort, key bits only)
-//   3. k_bucket_bounds     first sorted position of every bucket
-//   4. k_bucket_accumulate one thread per bucket, XYZZ mixed additions over gathered affine points
-//   5. k_bucket_reduce     per window: segmented running sums + block tree reduction
-//   6. k_window_combine    Horner over the windows -> one XYZZ point
-#include <cub/device/device_radix_sort.cuh>
+//   k_bucket_accumulate  one thread per work item (<= T mixed additions, items sorted by length), gathered
+//                        affine loads (16-byte vectors), XYZZ accumulator in registers
+//   k_bucket_fixup       buckets that were split into several items: block-wide tree sum of their partials
+//   k_bucket_reduce      sum_k (k+1) B_k per bucket set: segmented running sums + block tree reduction
+//   k_window_combine     plain layout: Horner over the windows;  k_final_sum: precomputed layout: tree sum
+//   k_build_table        precomputed layout: 2^(c w) P_i for every window, batch-normalised to affine
 #pragma once
 #include "msm.cuh"
 #include "msm_digits.cuh"
@@ -48,56 +47,37 @@ __device__ __forceinline__ void st_vec(T* p, const T& v) {
   for (int i = 0; i < (int)(sizeof(T) / 16); i++) q[i] = s[i];
 }
 
-// ---------------------------------------------------------------------------------------
-// 1. digits
-// ---------------------------------------------------------------------------------------
-static __global__ void k_msm_digits(const Fr* __restrict__ scalars, uint32_t n, int mont, int c, int nwin, uint32_t nb,
-                             uint32_t key_none, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fr s = ld_vec(scalars + i);
-  if (mont) s = from_mont(s);                    // msm.nim:44 toBig()
-  int carry = 0;
-  for (int w = 0; w < nwin; w++) {
-    int d = msm_signed_digit(s.v, c, w, nwin, carry);
-    uint32_t key = key_none, val = i;
-    if (d > 0) key = (uint32_t)w * nb + (uint32_t)(d - 1);
-    else if (d < 0) {
-      key = (uint32_t)w * nb + (uint32_t)(-d - 1);
-      val |= 0x80000000u;
-    }
-    keys[(size_t)w * n + i] = key;
-    vals[(size_t)w * n + i] = val;
-  }
-}
+template <class F>
+struct AccSets {
+  const Affine<F>* points[MsmAccumulator<F>::MAX_SETS];
+  XYZZ<F>* buckets[MsmAccumulator<F>::MAX_SETS];
+  XYZZ<F>* partials[MsmAccumulator<F>::MAX_SETS];
+  XYZZ<F>* winpart[MsmAccumulator<F>::MAX_SETS];
+  XYZZ<F>* result[MsmAccumulator<F>::MAX_SETS];
+};
 
 // ---------------------------------------------------------------------------------------
-// 3. bucket boundaries: start[b] = first j with keys[j] >= b
-// ---------------------------------------------------------------------------------------
-static __global__ void k_bucket_bounds(const uint32_t* __restrict__ keys, size_t m, uint32_t nbuckets,
-                                uint32_t* __restrict__ start) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > nbuckets) return;
-  size_t lo = 0, hi = m;
-  while (lo < hi) {
-    size_t mid = (lo + hi) >> 1;
-    if (keys[mid] < b) lo = mid + 1;
-    else hi = mid;
-  }
-  start[b] = (uint32_t)lo;
-}
-
-// ---------------------------------------------------------------------------------------
-// 4. bucket accumulation
+// bucket accumulation
 // ---------------------------------------------------------------------------------------
 template <class F>
-__global__ void __launch_bounds__(128) k_bucket_accumulate(const uint32_t* __restrict__ vals,
+__global__ void __launch_bounds__(128) k_bucket_accumulate(AccSets<F> sets, const uint32_t* __restrict__ vals,
                                                            const uint32_t* __restrict__ start,
-                                                           const Affine<F>* __restrict__ points,
-                                                           XYZZ<F>* __restrict__ buckets, uint32_t nbuckets) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nbuckets) return;
-  uint32_t j0 = start[b], j1 = start[b + 1];
+                                                           const uint32_t* __restrict__ item_start,
+                                                           const uint32_t* __restrict__ item_bucket,
+                                                           const uint32_t* __restrict__ items_sorted,
+                                                           uint32_t nbuckets, uint32_t max_items, uint32_t T) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= max_items) return;
+  uint32_t id = items_sorted[t];
+  if (id >= item_start[nbuckets]) return;          // padding
+  const int set = blockIdx.y;
+  const Affine<F>* __restrict__ points = sets.points[set];
+  uint32_t b = item_bucket[id];
+  uint32_t i0 = item_start[b];
+  uint32_t nitems = item_start[b + 1] - i0;
+  uint32_t j0 = start[b] + (id - i0) * T;
+  uint32_t j1 = start[b + 1];
+  if (j1 > j0 + T) j1 = j0 + T;
   XYZZ<F> acc = xyzz_inf<F>();
   for (uint32_t j = j0; j < j1; j++) {
     uint32_t v = vals[j];
@@ -105,22 +85,56 @@ __global__ void __launch_bounds__(128) k_bucket_accumulate(const uint32_t* __res
     if (v & 0x80000000u) p.y = fneg(p.y);
     acc = xyzz_madd(acc, p);
   }
-  st_vec(buckets + b, acc);
+  if (nitems == 1) st_vec(sets.buckets[set] + b, acc);
+  else st_vec(sets.partials[set] + id, acc);
+}
+
+// buckets split into several work items: sum their partials (rare; skewed scalar distributions)
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_fixup(AccSets<F> sets, const uint32_t* __restrict__ item_start,
+                                                      const uint32_t* __restrict__ multi_count,
+                                                      const uint32_t* __restrict__ multi_list) {
+  extern __shared__ uint4 red_raw[];
+  XYZZ<F>* red = reinterpret_cast<XYZZ<F>*>(red_raw);
+  const int set = blockIdx.y;
+  const uint32_t count = *multi_count;
+  for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
+    uint32_t b = multi_list[i];
+    uint32_t i0 = item_start[b], i1 = item_start[b + 1];
+    XYZZ<F> acc = xyzz_inf<F>();
+    for (uint32_t k = i0 + threadIdx.x; k < i1; k += blockDim.x) {
+      XYZZ<F> o = ld_vec(sets.partials[set] + k);
+      xyzz_add_ni(acc, acc, o);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+      if (threadIdx.x < s) {
+        XYZZ<F> o = red[threadIdx.x + s];
+        xyzz_add_ni(acc, acc, o);
+        red[threadIdx.x] = acc;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) st_vec(sets.buckets[set] + b, acc);
+    __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------------------
-// 5. bucket reduction: window sum = sum_k (k+1) * B_k
-//    thread t of a window owns buckets [t*L, (t+1)*L): running sums give
-//    S_t = sum B_k and R_t = sum (k - t*L + 1) B_k; its contribution is R_t + (t*L) * S_t.
+// bucket reduction: per bucket set, sum_k (k+1) * B_k
+//    thread t owns buckets [t*L, (t+1)*L): running sums give S_t = sum B_k and
+//    R_t = sum (k - t*L + 1) B_k; its contribution is R_t + (t*L) * S_t.
+// grid = (blocks per bucket set, bucket sets (windows), point sets)
 // ---------------------------------------------------------------------------------------
 template <class F>
-__global__ void __launch_bounds__(128) k_bucket_reduce(const XYZZ<F>* __restrict__ buckets, uint32_t nb, uint32_t L,
-                                                       XYZZ<F>* __restrict__ winpart) {
+__global__ void __launch_bounds__(128) k_bucket_reduce(AccSets<F> sets, uint32_t nb, uint32_t L) {
   extern __shared__ uint4 red_raw[];
   XYZZ<F>* red = reinterpret_cast<XYZZ<F>*>(red_raw);
   const uint32_t w = blockIdx.y;
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;     // segment index inside the window
-  const XYZZ<F>* B = buckets + (size_t)w * nb + (size_t)t * L;
+  const int set = blockIdx.z;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;     // segment index inside the bucket set
+  const XYZZ<F>* B = sets.buckets[set] + (size_t)w * nb + (size_t)t * L;
   XYZZ<F> running = xyzz_inf<F>(), sum = xyzz_inf<F>();
   for (int k = (int)L - 1; k >= 0; k--) {
     XYZZ<F> b = ld_vec(B + k);
@@ -141,22 +155,20 @@ __global__ void __launch_bounds__(128) k_bucket_reduce(const XYZZ<F>* __restrict
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) st_vec(winpart + (size_t)w * gridDim.x + blockIdx.x, red[0]);
+  if (threadIdx.x == 0) st_vec(sets.winpart[set] + (size_t)w * gridDim.x + blockIdx.x, sum);
 }
 
-// ---------------------------------------------------------------------------------------
-// 6. window combine: result = sum_w 2^(c w) * W_w  (Horner from the top window)
-// ---------------------------------------------------------------------------------------
+// plain layout: result = sum_w 2^(c w) * W_w  (Horner from the top window); grid.x = point sets
 template <class F>
-__global__ void k_window_combine(const XYZZ<F>* __restrict__ winpart, uint32_t bpw, int nwin, int c,
-                                 XYZZ<F>* __restrict__ result) {
+__global__ void k_window_combine(AccSets<F> sets, uint32_t bpw, int nwin, int c) {
   extern __shared__ uint4 red_raw[];
   XYZZ<F>* win = reinterpret_cast<XYZZ<F>*>(red_raw);
+  const int set = blockIdx.x;
   int w = threadIdx.x;
   if (w < nwin) {
     XYZZ<F> acc = xyzz_inf<F>();
     for (uint32_t i = 0; i < bpw; i++) {
-      XYZZ<F> o = ld_vec(winpart + (size_t)w * bpw + i);
+      XYZZ<F> o = ld_vec(sets.winpart[set] + (size_t)w * bpw + i);
       xyzz_add_ni(acc, acc, o);
     }
     win[w] = acc;
@@ -169,8 +181,32 @@ __global__ void k_window_combine(const XYZZ<F>* __restrict__ winpart, uint32_t b
       XYZZ<F> o = win[i];
       xyzz_add_ni(acc, acc, o);
     }
-    st_vec(result, acc);
+    st_vec(sets.result[set], acc);
   }
+}
+
+// precomputed layout: result = tree sum of the `count` block partials; grid.x = point sets
+template <class F>
+__global__ void __launch_bounds__(128) k_final_sum(AccSets<F> sets, uint32_t count) {
+  extern __shared__ uint4 red_raw[];
+  XYZZ<F>* red = reinterpret_cast<XYZZ<F>*>(red_raw);
+  const int set = blockIdx.x;
+  XYZZ<F> acc = xyzz_inf<F>();
+  for (uint32_t k = threadIdx.x; k < count; k += blockDim.x) {
+    XYZZ<F> o = ld_vec(sets.winpart[set] + k);
+    xyzz_add_ni(acc, acc, o);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      XYZZ<F> o = red[threadIdx.x + s];
+      xyzz_add_ni(acc, acc, o);
+      red[threadIdx.x] = acc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_vec(sets.result[set], acc);
 }
 
 template <class F>
@@ -191,130 +227,214 @@ __global__ void k_xyzz_sum_to_affine(const XYZZ<F>* parts, int count, Affine<F>*
   st_vec(out, a);
 }
 
+// ---------------------------------------------------------------------------------------
+// precomputed window table: one thread per point, c doublings per window, one batched inversion
+// ---------------------------------------------------------------------------------------
+constexpr int MSM_MAX_WINDOWS = 128;
+
 template <class F>
-__global__ void k_affine_sum_to_xyzz(const Affine<F>* parts, int count, XYZZ<F>* out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  XYZZ<F> acc = xyzz_inf<F>();
-  for (int i = 0; i < count; i++) {                                          // msm.nim:117-119
-    Affine<F> o = ld_vec(parts + i);
-    xyzz_madd_ni(acc, acc, o);
+__global__ void __launch_bounds__(128) k_build_table(const Affine<F>* __restrict__ points, uint32_t n_points,
+                                                     uint32_t pad_front, int c, int nwin,
+                                                     Affine<F>* __restrict__ table) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = n_points + pad_front;
+  if (i >= n) return;
+  if (i < pad_front) {
+    for (int w = 0; w < nwin; w++) st_vec(table + (size_t)w * n + i, aff_inf<F>());
+    return;
   }
-  st_vec(out, acc);
+  Affine<F> p = ldg_vec(points + (i - pad_front));
+  st_vec(table + i, p);
+  if (aff_is_inf(p)) {
+    for (int w = 1; w < nwin; w++) st_vec(table + (size_t)w * n + i, aff_inf<F>());
+    return;
+  }
+  // Montgomery's batch-inversion trick over the nwin-1 values t_w = zz_w * zzz_w of this point's doubling
+  // chain, with the table itself as scratch (no extra memory): the chain is walked twice.
+  // pass 1: forward walk; slot_w = (prefix product t_1..t_{w-1}, t_w)
+  XYZZ<F> q = xyzz_from_affine(p);
+  F prod = F::one();
+  for (int w = 1; w < nwin; w++) {
+    for (int j = 0; j < c; j++) xyzz_dbl_ni(q, q);
+    // BN254 G1/G2 have odd order: 2^k P is never infinity for P != infinity, so t_w != 0
+    Affine<F> slot;
+    slot.x = prod;
+    slot.y = fmul(q.zz, q.zzz);
+    st_vec(table + (size_t)w * n + i, slot);
+    prod = fmul(prod, slot.y);
+  }
+  F inv_all = finv(prod);
+  // pass 2: backward over the slots; 1/t_w = inv_all * prefix_w * suffix_w
+  q = xyzz_from_affine(p);
+  F suffix = F::one();
+  for (int w = nwin - 1; w >= 1; w--) {
+    Affine<F> slot = ld_vec(table + (size_t)w * n + i);
+    F t = slot.y;
+    slot.y = fmul(fmul(inv_all, slot.x), suffix);   // = 1 / t_w
+    st_vec(table + (size_t)w * n + i, slot);
+    suffix = fmul(suffix, t);
+  }
+  // pass 3: forward walk again, normalising each multiple with its stored inverse
+  for (int w = 1; w < nwin; w++) {
+    for (int j = 0; j < c; j++) xyzz_dbl_ni(q, q);
+    Affine<F> slot = ld_vec(table + (size_t)w * n + i);
+    F it = slot.y;                                   // 1 / (zz * zzz)
+    Affine<F> a;
+    a.x = fmul(q.x, fmul(it, q.zzz));                // X / zz
+    a.y = fmul(q.y, fmul(it, q.zz));                 // Y / zzz
+    st_vec(table + (size_t)w * n + i, a);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
-// host driver
+// host drivers
 // ---------------------------------------------------------------------------------------
 template <class F>
-size_t Msm<F>::workspace_bytes() const {
-  return keys_[0].bytes + keys_[1].bytes + vals_[0].bytes + vals_[1].bytes + start_.bytes + buckets_.bytes +
-         winpart_.bytes + cub_tmp_.bytes;
-}
-
-template <class F>
-Msm<F>::~Msm() {
-  for (int i = 0; i < 4; i++)
+MsmAccumulator<F>::~MsmAccumulator() {
+  for (int i = 0; i < 2; i++)
     if (pev_[i]) cudaEventDestroy(pev_[i]);
 }
 template <class F>
-float Msm<F>::last_accum_ms() const {
+size_t MsmAccumulator<F>::workspace_bytes() const {
+  return buckets_.bytes + partials_.bytes + winpart_.bytes;
+}
+template <class F>
+float MsmAccumulator<F>::last_accum_ms() const {
   float ms = 0.f;
-  if (pev_[1] && pev_[2]) cudaEventElapsedTime(&ms, pev_[1], pev_[2]);
+  if (pev_[0] && pev_[1]) cudaEventElapsedTime(&ms, pev_[0], pev_[1]);
   return ms;
+}
+
+template <class F>
+void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, int nsets, cudaStream_t stream) {
+  G16_REQUIRE(nsets >= 1 && nsets <= MAX_SETS, "MsmAccumulator: 1..3 point sets");
+  const MsmGeometry& g = sorter.geom();
+  G16_REQUIRE(g.nwin <= MSM_MAX_WINDOWS, "too many windows");
+  // reduction geometry: segments of L buckets, 128 segments per block
+  uint32_t L = g.nb < 16u ? 1u : 16u;
+  uint32_t nseg = g.nb / L;
+  uint32_t tpb = nseg < 128u ? nseg : 128u;
+  uint32_t bpw = nseg / tpb;                       // blocks (partial sums) per bucket set
+  uint32_t nsetsB = g.precomp ? 1u : (uint32_t)g.nwin;
+
+  size_t bucket_bytes = (size_t)g.nbuckets * sizeof(XYZZ<F>);
+  size_t partial_bytes = (size_t)g.max_items * sizeof(XYZZ<F>);
+  size_t winpart_bytes = (size_t)nsetsB * bpw * sizeof(XYZZ<F>);
+  buckets_.ensure(bucket_bytes * nsets);
+  partials_.ensure(partial_bytes * nsets);
+  winpart_.ensure(winpart_bytes * nsets);
+  AccSets<F> sets;
+  for (int s = 0; s < MAX_SETS; s++) {
+    int k = s < nsets ? s : 0;
+    sets.points[s] = in[k].points;
+    sets.result[s] = in[k].result;
+    sets.buckets[s] = reinterpret_cast<XYZZ<F>*>(buckets_.as<char>() + bucket_bytes * k);
+    sets.partials[s] = reinterpret_cast<XYZZ<F>*>(partials_.as<char>() + partial_bytes * k);
+    sets.winpart[s] = reinterpret_cast<XYZZ<F>*>(winpart_.as<char>() + winpart_bytes * k);
+  }
+  // empty buckets are never written by a work item: zero bytes == infinity
+  G16_CUDA(cudaMemsetAsync(buckets_.p, 0, bucket_bytes * nsets, stream));
+  if (profile) {
+    for (int i = 0; i < 2; i++)
+      if (!pev_[i]) G16_CUDA(cudaEventCreate(&pev_[i]));
+    G16_CUDA(cudaEventRecord(pev_[0], stream));
+  }
+  dim3 agrid(div_up(g.max_items, 128), (unsigned)nsets);
+  k_bucket_accumulate<F><<<agrid, 128, 0, stream>>>(sets, sorter.vals(), sorter.start(), sorter.item_start(),
+                                                   sorter.item_bucket(), sorter.items_sorted(), g.nbuckets,
+                                                   g.max_items, g.T);
+  G16_LAUNCH_CHECK();
+  if (profile) G16_CUDA(cudaEventRecord(pev_[1], stream));
+  dim3 fgrid(148, (unsigned)nsets);
+  k_bucket_fixup<F><<<fgrid, 128, 128 * sizeof(XYZZ<F>), stream>>>(sets, sorter.item_start(), sorter.multi_count(),
+                                                                   sorter.multi_list());
+  G16_LAUNCH_CHECK();
+  dim3 rgrid(bpw, nsetsB, (unsigned)nsets);
+  k_bucket_reduce<F><<<rgrid, tpb, tpb * sizeof(XYZZ<F>), stream>>>(sets, g.nb, L);
+  G16_LAUNCH_CHECK();
+  if (g.precomp) {
+    k_final_sum<F><<<nsets, 128, 128 * sizeof(XYZZ<F>), stream>>>(sets, bpw);
+  } else {
+    int cthreads = ((g.nwin + 31) / 32) * 32;
+    k_window_combine<F><<<nsets, cthreads, (size_t)g.nwin * sizeof(XYZZ<F>), stream>>>(sets, bpw, g.nwin, g.c);
+  }
+  G16_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------
+template <class F>
+Msm<F>::~Msm() {
+  for (int i = 0; i < 2; i++)
+    if (tev_[i]) cudaEventDestroy(tev_[i]);
 }
 template <class F>
 float Msm<F>::last_total_ms() const {
   float ms = 0.f;
-  if (pev_[0] && pev_[3]) cudaEventElapsedTime(&ms, pev_[0], pev_[3]);
+  if (tev_[0] && tev_[1]) cudaEventElapsedTime(&ms, tev_[0], tev_[1]);
   return ms;
 }
 
 template <class F>
-void Msm<F>::run(const Fr* scalars, bool scalars_mont, const Affine<F>* points, size_t n, XYZZ<F>* result,
-                 cudaStream_t stream, const MsmConfig& cfg) {
-  G16_REQUIRE(n < ((size_t)1 << 31), "MSM size must be below 2^31");
-  if (n == 0) {                                   // zero-length MSM (C1 when nvars = npubs+1)
-    k_set_inf<F><<<1, 32, 0, stream>>>(result);
-    G16_LAUNCH_CHECK();
-    return;
+void Msm<F>::go(const Fr* scalars, bool mont, const Affine<F>* pts, const MsmGeometry& g, XYZZ<F>* result,
+                cudaStream_t stream) {
+  last_c = g.c;
+  last_nwin = g.nwin;
+  if (profile_) {
+    for (int i = 0; i < 2; i++)
+      if (!tev_[i]) G16_CUDA(cudaEventCreate(&tev_[i]));
+    G16_CUDA(cudaEventRecord(tev_[0], stream));
   }
-  const int c = cfg.c ? cfg.c : msm_pick_window(n, sizeof(F) > sizeof(Fp));
-  G16_REQUIRE(c >= 2 && c <= 22, "MSM window must be 2..22 bits");
-  const int nwin = msm_num_windows(c);
-  const uint32_t nb = 1u << (c - 1);
-  const uint32_t nbuckets = (uint32_t)nwin * nb;
-  const size_t m = (size_t)nwin * n;
-  G16_REQUIRE(m < ((size_t)1 << 32), "MSM pair count must fit 32 bits");
-  last_c = c;
-  last_nwin = nwin;
-  if (profile) {
-    for (int i = 0; i < 4; i++)
-      if (!pev_[i]) G16_CUDA(cudaEventCreate(&pev_[i]));
-    G16_CUDA(cudaEventRecord(pev_[0], stream));
-  }
-
-  keys_[0].ensure(m * 4);
-  keys_[1].ensure(m * 4);
-  vals_[0].ensure(m * 4);
-  vals_[1].ensure(m * 4);
-  start_.ensure(((size_t)nbuckets + 2) * 4);
-  buckets_.ensure((size_t)nbuckets * sizeof(XYZZ<F>));
-
-  // bucket reduction geometry
-  uint32_t nseg = nb < 2048u ? nb : 2048u;       // segments (threads) per window
-  uint32_t L = nb / nseg;
-  uint32_t tpb = nseg < 128u ? nseg : 128u;
-  uint32_t bpw = nseg / tpb;
-  winpart_.ensure((size_t)nwin * bpw * sizeof(XYZZ<F>));
-
-  k_msm_digits<<<div_up(n, 256), 256, 0, stream>>>(scalars, (uint32_t)n, scalars_mont ? 1 : 0, c, nwin, nb, nbuckets,
-                                                   keys_[0].as<uint32_t>(), vals_[0].as<uint32_t>());
-  G16_LAUNCH_CHECK();
-
-  int end_bit = 1;
-  while (((uint64_t)1 << end_bit) <= (uint64_t)nbuckets) end_bit++;
-  size_t tmp_bytes = 0;
-  G16_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_[0].as<uint32_t>(), keys_[1].as<uint32_t>(),
-                                           vals_[0].as<uint32_t>(), vals_[1].as<uint32_t>(), (int64_t)m, 0, end_bit,
-                                           stream));
-  cub_tmp_.ensure(tmp_bytes);
-  G16_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp_.p, tmp_bytes, keys_[0].as<uint32_t>(), keys_[1].as<uint32_t>(),
-                                           vals_[0].as<uint32_t>(), vals_[1].as<uint32_t>(), (int64_t)m, 0, end_bit,
-                                           stream));
-
-  k_bucket_bounds<<<div_up((size_t)nbuckets + 1, 256), 256, 0, stream>>>(keys_[1].as<uint32_t>(), m, nbuckets,
-                                                                         start_.as<uint32_t>());
-  G16_LAUNCH_CHECK();
-  if (profile) G16_CUDA(cudaEventRecord(pev_[1], stream));
-  k_bucket_accumulate<F><<<div_up(nbuckets, 128), 128, 0, stream>>>(vals_[1].as<uint32_t>(), start_.as<uint32_t>(),
-                                                                    points, buckets_.as<XYZZ<F>>(), nbuckets);
-  G16_LAUNCH_CHECK();
-  if (profile) G16_CUDA(cudaEventRecord(pev_[2], stream));
-  dim3 rgrid(bpw, (unsigned)nwin);
-  k_bucket_reduce<F><<<rgrid, tpb, tpb * sizeof(XYZZ<F>), stream>>>(buckets_.as<XYZZ<F>>(), nb, L,
-                                                                    winpart_.as<XYZZ<F>>());
-  G16_LAUNCH_CHECK();
-  int cthreads = ((nwin + 31) / 32) * 32;
-  k_window_combine<F><<<1, cthreads, (size_t)nwin * sizeof(XYZZ<F>), stream>>>(winpart_.as<XYZZ<F>>(), bpw, nwin, c,
-                                                                               result);
-  G16_LAUNCH_CHECK();
-  if (profile) {
-    G16_CUDA(cudaEventRecord(pev_[3], stream));
+  sorter_.run(scalars, mont, g, stream);
+  MsmPointSet<F> set;
+  set.points = pts;
+  set.result = result;
+  acc_.run(sorter_, &set, 1, stream);
+  if (profile_) {
+    G16_CUDA(cudaEventRecord(tev_[1], stream));
     uint32_t pairs = 0;   // start[nbuckets] = number of sorted pairs with a real bucket key
-    G16_CUDA(cudaMemcpyAsync(&pairs, start_.as<uint32_t>() + nbuckets, 4, cudaMemcpyDeviceToHost, stream));
+    G16_CUDA(cudaMemcpyAsync(&pairs, sorter_.start() + g.nbuckets, 4, cudaMemcpyDeviceToHost, stream));
     G16_CUDA(cudaStreamSynchronize(stream));
     last_pairs = pairs;
   }
 }
 
 template <class F>
-void xyzz_sum_to_affine(const XYZZ<F>* parts, int count, Affine<F>* out, cudaStream_t stream) {
-  k_xyzz_sum_to_affine<F><<<1, 32, 0, stream>>>(parts, count, out);
+void Msm<F>::run(const Fr* scalars, bool scalars_mont, const Affine<F>* points, size_t n, XYZZ<F>* result,
+                 cudaStream_t stream, int window_bits) {
+  if (n == 0) {                                   // zero-length MSM (C1 when nvars = npubs+1)
+    k_set_inf<F><<<1, 32, 0, stream>>>(result);
+    G16_LAUNCH_CHECK();
+    return;
+  }
+  int c = window_bits ? window_bits : msm_pick_window(n, false);
+  go(scalars, scalars_mont, points, msm_geometry(n, c, false), result, stream);
+}
+
+template <class F>
+void Msm<F>::run_precomp(const Fr* scalars, bool scalars_mont, const Affine<F>* table, size_t n, int window_bits,
+                         XYZZ<F>* result, cudaStream_t stream) {
+  if (n == 0) {
+    k_set_inf<F><<<1, 32, 0, stream>>>(result);
+    G16_LAUNCH_CHECK();
+    return;
+  }
+  go(scalars, scalars_mont, table, msm_geometry(n, window_bits, true), result, stream);
+}
+
+template <class F>
+void msm_build_table(const Affine<F>* points, size_t n_points, size_t pad_front, int c, Affine<F>* table,
+                     cudaStream_t stream) {
+  size_t n = n_points + pad_front;
+  if (!n) return;
+  int nwin = msm_num_windows(c);
+  k_build_table<F><<<div_up(n, 128), 128, 0, stream>>>(points, (uint32_t)n_points, (uint32_t)pad_front, c, nwin,
+                                                       table);
   G16_LAUNCH_CHECK();
 }
+
 template <class F>
-void affine_sum_to_xyzz(const Affine<F>* parts, int count, XYZZ<F>* out, cudaStream_t stream) {
-  k_affine_sum_to_xyzz<F><<<1, 32, 0, stream>>>(parts, count, out);
+void xyzz_sum_to_affine(const XYZZ<F>* parts, int count, Affine<F>* out, cudaStream_t stream) {
+  k_xyzz_sum_to_affine<F><<<1, 32, 0, stream>>>(parts, count, out);
   G16_LAUNCH_CHECK();
 }
 

@@ -1,0 +1,220 @@
+// MSM front end shared by every point set over the same scalars: signed-digit decomposition, radix sort of
+// (bucket, point reference) pairs, bucket boundaries and length-balanced work items.
+//
+//   k_msm_digits       one thread per scalar: window digits -> keys[w*n+i] (bucket), vals[w*n+i] (point | sign)
+//   CUB radix sort     pairs by bucket key (only the significant key bits)
+//   k_bucket_bounds    start[b] = first sorted position with key >= b
+//   k_bucket_chunks    a bucket longer than T additions is split into ceil(len/T) work items
+//   CUB exclusive sum  item_start[b]
+//   k_make_items       item -> bucket, sort key = T - length (longest first); multi-item buckets are listed
+//   CUB radix sort     items by length so the 32 lanes of a warp run equally long loops
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include "msm.cuh"
+#include "msm_digits.cuh"
+
+namespace g16 {
+
+int msm_pick_window(size_t n, bool precomp) {
+  double best = 1e300;
+  int best_c = 4;
+  for (int c = 4; c <= 22; c++) {
+    double W = (double)msm_num_windows(c);
+    double nb = (double)((size_t)1 << (c - 1));
+    double sets = precomp ? 1.0 : W;
+    // mixed additions (10 modmul) per pair + running sums (2 full additions of 14 modmul per bucket)
+    // + sort / launch overheads that grow with the pair and bucket counts
+    double cost = 10.0 * W * (double)n + 28.0 * sets * nb + 0.6 * W * (double)n + 4000.0 * sets;
+    if (!precomp && c > 18) continue;
+    if (W * (double)n >= 2147483648.0) continue;   // point references are 31 bits
+    if (cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  return best_c;
+}
+
+MsmGeometry msm_geometry(size_t n, int c, bool precomp) {
+  G16_REQUIRE(n < ((size_t)1 << 31), "MSM size must be below 2^31");
+  G16_REQUIRE(c >= 2 && c <= 22, "MSM window must be 2..22 bits");
+  MsmGeometry g;
+  g.n = n;
+  g.c = c;
+  g.nwin = msm_num_windows(c);
+  g.precomp = precomp;
+  g.nb = 1u << (c - 1);
+  g.nbuckets = precomp ? g.nb : (uint32_t)g.nwin * g.nb;
+  g.m = (size_t)g.nwin * n;
+  G16_REQUIRE(g.m < ((size_t)1 << 31), "MSM pair count must fit 31 bits");
+  size_t avg = g.m / g.nbuckets + 1;
+  size_t T = 4 * avg;
+  if (T < 64) T = 64;
+  if (T > 32768) T = 32768;
+  g.T = (uint32_t)T;
+  g.max_items = g.nbuckets + (uint32_t)(g.m / T) + 1;
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------
+static __device__ __forceinline__ Fr ld_scalar(const Fr* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+__global__ void k_msm_digits(const Fr* __restrict__ scalars, uint32_t n, int mont, int c, int nwin, uint32_t nb,
+                             int precomp, uint32_t key_none, uint32_t* __restrict__ keys,
+                             uint32_t* __restrict__ vals) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = ld_scalar(scalars + i);
+  if (mont) s = from_mont(s);                    // msm.nim:44 toBig()
+  int carry = 0;
+  for (int w = 0; w < nwin; w++) {
+    int d = msm_signed_digit(s.v, c, w, nwin, carry);
+    uint32_t ref = precomp ? (uint32_t)w * n + i : i;
+    uint32_t base = precomp ? 0u : (uint32_t)w * nb;
+    uint32_t key = key_none;
+    if (d > 0) key = base + (uint32_t)(d - 1);
+    else if (d < 0) {
+      key = base + (uint32_t)(-d - 1);
+      ref |= 0x80000000u;
+    }
+    keys[(size_t)w * n + i] = key;
+    vals[(size_t)w * n + i] = ref;
+  }
+}
+
+__global__ void k_bucket_bounds(const uint32_t* __restrict__ keys, uint32_t m, uint32_t nbuckets,
+                                uint32_t* __restrict__ start) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nbuckets) return;
+  uint32_t lo = 0, hi = m;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (keys[mid] < b) lo = mid + 1;
+    else hi = mid;
+  }
+  start[b] = lo;
+}
+
+__global__ void k_bucket_chunks(const uint32_t* __restrict__ start, uint32_t nbuckets, uint32_t T,
+                                uint32_t* __restrict__ chunks) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nbuckets) return;
+  uint32_t len = b < nbuckets ? start[b + 1] - start[b] : 0;
+  chunks[b] = (len + T - 1) / T;
+}
+
+__global__ void k_items_init(uint32_t* __restrict__ key, uint32_t* __restrict__ idx, uint32_t max_items, uint32_t T,
+                             uint32_t* __restrict__ multi_count) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) *multi_count = 0;
+  if (t >= max_items) return;
+  key[t] = T;        // padding sorts after every real item (real keys are T - len <= T - 1)
+  idx[t] = t;
+}
+
+__global__ void k_make_items(const uint32_t* __restrict__ start, const uint32_t* __restrict__ item_start,
+                             uint32_t nbuckets, uint32_t T, uint32_t* __restrict__ item_bucket,
+                             uint32_t* __restrict__ item_key, uint32_t* __restrict__ multi) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbuckets) return;
+  uint32_t i0 = item_start[b], i1 = item_start[b + 1];
+  if (i1 == i0) return;
+  uint32_t len = start[b + 1] - start[b];
+  for (uint32_t k = 0; i0 + k < i1; k++) {
+    uint32_t l = len - k * T;
+    if (l > T) l = T;
+    item_bucket[i0 + k] = b;
+    item_key[i0 + k] = T - l;
+  }
+  if (i1 - i0 > 1) {
+    uint32_t slot = atomicAdd(multi, 1u);
+    multi[1 + slot] = b;
+  }
+}
+
+MsmSorter::~MsmSorter() {}
+
+size_t MsmSorter::workspace_bytes() const {
+  size_t t = 0;
+  const DevBuf* all[] = {&keys_[0], &keys_[1], &vals_[0], &vals_[1], &start_, &chunks_, &item_start_, &item_bucket_,
+                         &item_key_[0], &item_key_[1], &item_idx_[0], &item_idx_[1], &multi_, &cub_tmp_};
+  for (auto* b : all) t += b->bytes;
+  return t;
+}
+
+static int bits_for(uint64_t max_value) {
+  int b = 1;
+  while (((uint64_t)1 << b) <= max_value) b++;
+  return b;
+}
+
+void MsmSorter::run(const Fr* scalars, bool scalars_mont, const MsmGeometry& g, cudaStream_t stream) {
+  g_ = g;
+  G16_REQUIRE(g.n > 0, "MsmSorter: empty input");
+  const size_t m = g.m;
+  keys_[0].ensure(m * 4);
+  keys_[1].ensure(m * 4);
+  vals_[0].ensure(m * 4);
+  vals_[1].ensure(m * 4);
+  start_.ensure(((size_t)g.nbuckets + 2) * 4);
+  chunks_.ensure(((size_t)g.nbuckets + 2) * 4);
+  item_start_.ensure(((size_t)g.nbuckets + 2) * 4);
+  item_bucket_.ensure((size_t)g.max_items * 4);
+  for (int i = 0; i < 2; i++) {
+    item_key_[i].ensure((size_t)g.max_items * 4);
+    item_idx_[i].ensure((size_t)g.max_items * 4);
+  }
+  multi_.ensure(((size_t)g.nbuckets + 2) * 4);
+
+  k_msm_digits<<<div_up(g.n, 256), 256, 0, stream>>>(scalars, (uint32_t)g.n, scalars_mont ? 1 : 0, g.c, g.nwin, g.nb,
+                                                     g.precomp ? 1 : 0, g.nbuckets, keys_[0].as<uint32_t>(),
+                                                     vals_[0].as<uint32_t>());
+  G16_LAUNCH_CHECK();
+
+  // temp storage: the larger of the three CUB calls
+  int key_bits = bits_for(g.nbuckets);
+  int item_bits = bits_for(g.T);
+  size_t t1 = 0, t2 = 0, t3 = 0;
+  G16_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, keys_[0].as<uint32_t>(), keys_[1].as<uint32_t>(),
+                                           vals_[0].as<uint32_t>(), vals_[1].as<uint32_t>(), (int64_t)m, 0, key_bits,
+                                           stream));
+  G16_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t2, chunks_.as<uint32_t>(), item_start_.as<uint32_t>(),
+                                         (int)(g.nbuckets + 1), stream));
+  G16_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t3, item_key_[0].as<uint32_t>(), item_key_[1].as<uint32_t>(),
+                                           item_idx_[0].as<uint32_t>(), item_idx_[1].as<uint32_t>(),
+                                           (int64_t)g.max_items, 0, item_bits, stream));
+  size_t tmp = t1 > t2 ? t1 : t2;
+  if (t3 > tmp) tmp = t3;
+  cub_tmp_.ensure(tmp);
+
+  G16_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp_.p, t1, keys_[0].as<uint32_t>(), keys_[1].as<uint32_t>(),
+                                           vals_[0].as<uint32_t>(), vals_[1].as<uint32_t>(), (int64_t)m, 0, key_bits,
+                                           stream));
+  k_bucket_bounds<<<div_up((size_t)g.nbuckets + 1, 256), 256, 0, stream>>>(keys_[1].as<uint32_t>(), (uint32_t)m,
+                                                                           g.nbuckets, start_.as<uint32_t>());
+  G16_LAUNCH_CHECK();
+  k_bucket_chunks<<<div_up((size_t)g.nbuckets + 1, 256), 256, 0, stream>>>(start_.as<uint32_t>(), g.nbuckets, g.T,
+                                                                           chunks_.as<uint32_t>());
+  G16_LAUNCH_CHECK();
+  G16_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp_.p, t2, chunks_.as<uint32_t>(), item_start_.as<uint32_t>(),
+                                         (int)(g.nbuckets + 1), stream));
+  k_items_init<<<div_up(g.max_items, 256), 256, 0, stream>>>(item_key_[0].as<uint32_t>(), item_idx_[0].as<uint32_t>(),
+                                                             g.max_items, g.T, multi_.as<uint32_t>());
+  G16_LAUNCH_CHECK();
+  k_make_items<<<div_up(g.nbuckets, 256), 256, 0, stream>>>(start_.as<uint32_t>(), item_start_.as<uint32_t>(),
+                                                            g.nbuckets, g.T, item_bucket_.as<uint32_t>(),
+                                                            item_key_[0].as<uint32_t>(), multi_.as<uint32_t>());
+  G16_LAUNCH_CHECK();
+  G16_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp_.p, t3, item_key_[0].as<uint32_t>(), item_key_[1].as<uint32_t>(),
+                                           item_idx_[0].as<uint32_t>(), item_idx_[1].as<uint32_t>(),
+                                           (int64_t)g.max_items, 0, item_bits, stream));
+}
+
+}  // namespace g16

@@ -1,12 +1,15 @@
 // Resident Groth16 proving context on one B200.
 //
 // Replaces generateProofWithMask (groth16/prover.nim:215-304): buildABC (:245), the quotient (:250-260),
-// the five MSMs (:279-302) and the proof assembly (:278-304).  The zkey's prover points and its
-// coefficient list are uploaded once (g16_ctx_create); per proof only the witness travels.  The five
-// MSMs are independent given the witness (A1, B1, B2, C1) and the quotient (H1), so they run on five
-// streams; the mask terms that need no MSM result (r*delta1, s*delta1, s*delta2, -rs*delta1) run on a
-// sixth.  A context may own only the point range [N*k/G, N*(k+1)/G) of every MSM (msm.nim:107-115): then
-// run_msms() yields partial sums that the host side all-gathers between GPUs.
+// the five MSMs (:279-302) and the proof assembly (:278-304).  At g16_ctx_create the zkey's prover points
+// are expanded ONCE into window tables 2^(c w) P_i that stay resident in HBM (about 13x the point bytes --
+// 5 GB at 2^20, 21 GB at 2^22 of the 180 GB), and the coefficient list is sorted into CSR rows; per proof
+// only the witness travels.  The four witness MSMs (A1, B1, B2, C1) read the same scalars, so they share
+// one digit/sort pass (C1 is padded with npubs+1 infinities so its indices are witness indices) and the
+// three G1 sets are accumulated by the same launches; B2 and the H chain (ABC -> quotient -> sort -> H1)
+// run on their own streams; the mask terms that need no MSM result run on a fourth.  A context may own only
+// the point range [N*k/G, N*(k+1)/G) of every MSM (msm.nim:107-115): run_msms() then yields partial sums
+// that the host side all-gathers between GPUs.
 #include "prover.cuh"
 #include "ntt.cuh"
 
@@ -153,13 +156,30 @@ static void shard_range(size_t N, int k, int G, size_t& lo, size_t& hi) {   // m
   hi = (k == G - 1) ? N : (N * (size_t)(k + 1)) / (size_t)G;
 }
 
-static void upload(DevBuf& dst, const void* src, size_t elem, size_t lo, size_t hi, int mem_kind) {
+// raw points of [lo, hi) -> temporary device buffer.  The copy is issued on the consumer's stream: a plain
+// cudaMemcpy from pageable memory returns once the data is staged and is ordered only against the legacy
+// default stream, which non-blocking streams do not wait for.
+static void upload(DevBuf& dst, const void* src, size_t elem, size_t lo, size_t hi, int mem_kind,
+                   cudaStream_t stream) {
   size_t bytes = (hi - lo) * elem;
   dst.ensure(bytes ? bytes : 16);
   if (!bytes) return;
   G16_REQUIRE(src != nullptr, "zkey view: missing point array");
   const char* s = reinterpret_cast<const char*>(src) + lo * elem;
-  G16_CUDA(cudaMemcpy(dst.p, s, bytes, mem_kind == G16_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  G16_CUDA(cudaMemcpyAsync(dst.p, s, bytes,
+                           mem_kind == G16_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+}
+
+template <class F>
+static void make_table(DevBuf& table, const void* src, size_t lo, size_t hi, size_t pad_front, int c, int mem_kind,
+                       cudaStream_t stream) {
+  size_t n = (hi - lo) + pad_front;
+  table.ensure(n ? (size_t)msm_num_windows(c) * n * sizeof(Affine<F>) : 16);
+  if (!n) return;
+  DevBuf raw;
+  upload(raw, src, sizeof(Affine<F>), lo, hi, mem_kind, stream);
+  msm_build_table<F>(raw.as<Affine<F>>(), hi - lo, pad_front, c, table.as<Affine<F>>(), stream);
+  G16_CUDA(cudaStreamSynchronize(stream));   // raw is released on return
 }
 
 Prover::Prover(const g16_zkey_view& zk, int shard_index, int shard_count)
@@ -174,20 +194,29 @@ Prover::Prover(const g16_zkey_view& zk, int shard_index, int shard_count)
   flavour_ = zk.flavour;
   n_ = (size_t)1 << log_n_;
   for (int i = 0; i < 24; i++) ev_[i] = nullptr;
-
-  shard_range(nvars_, shard_index, shard_count, v_lo_, v_hi_);
-  shard_range((size_t)nvars_ - npubs_ - 1, shard_index, shard_count, c_lo_, c_hi_);
-  shard_range(n_, shard_index, shard_count, h_lo_, h_hi_);
-  upload(ptsA1_, zk.points_a1, sizeof(G1Affine), v_lo_, v_hi_, zk.mem_kind);
-  upload(ptsB1_, zk.points_b1, sizeof(G1Affine), v_lo_, v_hi_, zk.mem_kind);
-  upload(ptsB2_, zk.points_b2, sizeof(G2Affine), v_lo_, v_hi_, zk.mem_kind);
-  upload(ptsC1_, zk.points_c1, sizeof(G1Affine), c_lo_, c_hi_, zk.mem_kind);
-  upload(ptsH1_, zk.points_h1, sizeof(G1Affine), h_lo_, h_hi_, zk.mem_kind);
-
   G16_CUDA(cudaStreamCreateWithFlags(&main_, cudaStreamNonBlocking));
-  for (int i = 0; i < 5; i++) G16_CUDA(cudaStreamCreateWithFlags(&st_[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 3; i++) G16_CUDA(cudaStreamCreateWithFlags(&st_[i], cudaStreamNonBlocking));
   G16_CUDA(cudaStreamCreateWithFlags(&st_mask_, cudaStreamNonBlocking));
   for (int i = 0; i < 24; i++) G16_CUDA(cudaEventCreate(&ev_[i]));
+
+  // this context's contiguous ranges (msm.nim:107-111): witness-indexed arrays and the H array
+  shard_range(nvars_, shard_index, shard_count, v_lo_, v_hi_);
+  shard_range(n_, shard_index, shard_count, h_lo_, h_hi_);
+  const size_t nv = v_hi_ - v_lo_, nh = h_hi_ - h_lo_;
+  if (nv) gw_ = msm_geometry(nv, msm_pick_window(nv, true), true);
+  if (nh) gh_ = msm_geometry(nh, msm_pick_window(nh, true), true);
+  make_table<Fp>(tabA1_, zk.points_a1, v_lo_, v_hi_, 0, gw_.c ? gw_.c : 4, zk.mem_kind, main_);
+  make_table<Fp>(tabB1_, zk.points_b1, v_lo_, v_hi_, 0, gw_.c ? gw_.c : 4, zk.mem_kind, main_);
+  make_table<Fp2>(tabB2_, zk.points_b2, v_lo_, v_hi_, 0, gw_.c ? gw_.c : 4, zk.mem_kind, main_);
+  {
+    // C1[j - npubs - 1] multiplies witness[j] (prover.nim:262-264): pad so that table index == witness index
+    size_t first = (size_t)npubs_ + 1;
+    size_t from = v_lo_ > first ? v_lo_ : first;            // first witness index of this shard with a C point
+    size_t pad = v_hi_ > from ? from - v_lo_ : nv;
+    size_t c_lo = from - first, c_hi = v_hi_ > from ? v_hi_ - first : c_lo;
+    make_table<Fp>(tabC1_, zk.points_c1, c_lo, c_hi, pad, gw_.c ? gw_.c : 4, zk.mem_kind, main_);
+  }
+  make_table<Fp>(tabH1_, zk.points_h1, h_lo_, h_hi_, 0, gh_.c ? gh_.c : 4, zk.mem_kind, main_);
 
   // coefficient list -> CSR rows (once per zkey)
   {
@@ -196,8 +225,9 @@ Prover::Prover(const g16_zkey_view& zk, int shard_index, int shard_count)
     raw.ensure(zk.ncoeffs * rec + 16);
     if (zk.ncoeffs) {
       G16_REQUIRE(zk.coeffs != nullptr, "zkey view: missing coefficient list");
-      G16_CUDA(cudaMemcpy(raw.p, zk.coeffs, zk.ncoeffs * rec,
-                          zk.mem_kind == G16_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+      G16_CUDA(cudaMemcpyAsync(raw.p, zk.coeffs, zk.ncoeffs * rec,
+                               zk.mem_kind == G16_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                               main_));
     }
     coeffs_to_csr(csr_, raw.p, zk.ncoeffs, (int)zk.coeff_format, (int)log_n_, nvars_, main_);
   }
@@ -209,12 +239,14 @@ Prover::Prover(const g16_zkey_view& zk, int shard_index, int shard_count)
   memcpy(&sp.beta2, zk.beta2, 128);
   memcpy(&sp.delta2, zk.delta2, 128);
   spec_.ensure(sizeof(SpecPointsDev));
-  G16_CUDA(cudaMemcpy(spec_.p, &sp, sizeof(sp), cudaMemcpyHostToDevice));
+  G16_CUDA(cudaMemcpyAsync(spec_.p, &sp, sizeof(sp), cudaMemcpyHostToDevice, main_));
+  G16_CUDA(cudaStreamSynchronize(main_));
 
   witness_.ensure((size_t)nvars_ * sizeof(Fr));
   abc_.ensure(3 * n_ * sizeof(Fr));
   qs_.ensure(n_ * sizeof(Fr));
   results_.ensure(sizeof(MsmResults));
+  G16_CUDA(cudaMemset(results_.p, 0, sizeof(MsmResults)));   // all-zero XYZZ == infinity (empty shards)
   mask_.ensure(sizeof(MaskTerms));
   proof_.ensure(sizeof(g16_proof));
   G16_CUDA(cudaMallocHost(reinterpret_cast<void**>(&proof_pinned_), sizeof(g16_proof)));
@@ -222,11 +254,17 @@ Prover::Prover(const g16_zkey_view& zk, int shard_index, int shard_count)
   G16_CUDA(cudaStreamSynchronize(main_));
 }
 
+size_t Prover::resident_bytes() const {
+  return tabA1_.bytes + tabB1_.bytes + tabC1_.bytes + tabH1_.bytes + tabB2_.bytes + csr_.ptr.bytes + csr_.other.bytes +
+         csr_.vals.bytes + witness_.bytes + abc_.bytes + qs_.bytes + sortW_.workspace_bytes() +
+         sortH_.workspace_bytes() + accW_.workspace_bytes() + accH_.workspace_bytes() + accB2_.workspace_bytes();
+}
+
 Prover::~Prover() {
   cudaDeviceSynchronize();
   for (int i = 0; i < 24; i++)
     if (ev_[i]) cudaEventDestroy(ev_[i]);
-  for (int i = 0; i < 5; i++)
+  for (int i = 0; i < 3; i++)
     if (st_[i]) cudaStreamDestroy(st_[i]);
   if (st_mask_) cudaStreamDestroy(st_mask_);
   if (main_) cudaStreamDestroy(main_);
@@ -268,38 +306,59 @@ void Prover::load_witness(const void* w, int form, int mem_kind) {
 }
 
 void Prover::run_msms(g16_stats* stats) {
+  // empty shards write nothing: start every proof from infinity (all-zero XYZZ)
+  G16_CUDA(cudaMemsetAsync(results_.p, 0, sizeof(MsmResults), main_));
   // ev_[0]: witness ready on main_; every worker stream waits for it
   G16_CUDA(cudaEventRecord(ev_[0], main_));
-  for (int i = 0; i < 5; i++) G16_CUDA(cudaStreamWaitEvent(st_[i], ev_[0], 0));
+  for (int i = 0; i < 3; i++) G16_CUDA(cudaStreamWaitEvent(st_[i], ev_[0], 0));
   MsmResults* res = results_.as<MsmResults>();
   const Fr* w = witness_.as<Fr>();
+  const size_t nv = v_hi_ - v_lo_, nh = h_hi_ - h_lo_;
 
-  // stream 0: ABC -> quotient -> MSM over the H points   (prover.nim:245-260, 301)
+  // stream 0: ABC -> quotient -> sort of qs -> MSM over the H table   (prover.nim:245-260, 301)
   G16_CUDA(cudaEventRecord(ev_[1], st_[0]));
   build_abc(csr_, w, abc_.as<Fr>(), (int)log_n_, st_[0]);
   G16_CUDA(cudaEventRecord(ev_[2], st_[0]));
   quotient(abc_.as<Fr>(), qs_.as<Fr>(), (int)log_n_, (int)flavour_, st_[0]);
   G16_CUDA(cudaEventRecord(ev_[3], st_[0]));
-  msmH_.run(qs_.as<Fr>() + h_lo_, true, ptsH1_.as<G1Affine>(), h_hi_ - h_lo_, &res->h1, st_[0]);
+  if (nh) {
+    sortH_.run(qs_.as<Fr>() + h_lo_, true, gh_, st_[0]);
+    MsmPointSet<Fp> hs;
+    hs.points = tabH1_.as<G1Affine>();
+    hs.result = &res->h1;
+    accH_.run(sortH_, &hs, 1, st_[0]);
+  }
   G16_CUDA(cudaEventRecord(ev_[4], st_[0]));
-  // stream 1: pi_A MSM (prover.nim:282)
-  G16_CUDA(cudaEventRecord(ev_[5], st_[1]));
-  msmA_.run(w + v_lo_, false, ptsA1_.as<G1Affine>(), v_hi_ - v_lo_, &res->a1, st_[1]);
-  G16_CUDA(cudaEventRecord(ev_[6], st_[1]));
-  // stream 2: rho MSM (prover.nim:288)
-  G16_CUDA(cudaEventRecord(ev_[7], st_[2]));
-  msmB1_.run(w + v_lo_, false, ptsB1_.as<G1Affine>(), v_hi_ - v_lo_, &res->b1, st_[2]);
-  G16_CUDA(cudaEventRecord(ev_[8], st_[2]));
-  // stream 3: pi_B MSM in G2 (prover.nim:294)
-  G16_CUDA(cudaEventRecord(ev_[9], st_[3]));
-  msmB2_.run(w + v_lo_, false, ptsB2_.as<G2Affine>(), v_hi_ - v_lo_, &res->b2, st_[3]);
-  G16_CUDA(cudaEventRecord(ev_[10], st_[3]));
-  // stream 4: MSM over the C points with zs = witness[npubs+1 ..] (prover.nim:262-264, 302)
-  G16_CUDA(cudaEventRecord(ev_[11], st_[4]));
-  msmC_.run(w + npubs_ + 1 + c_lo_, false, ptsC1_.as<G1Affine>(), c_hi_ - c_lo_, &res->c1, st_[4]);
-  G16_CUDA(cudaEventRecord(ev_[12], st_[4]));
 
-  for (int i = 0; i < 5; i++) {
+  // stream 1: one digit/sort pass over the witness, then A1, B1, C1 in the same launches
+  // (prover.nim:282, 288, 302; zs = witness[npubs+1 ..] through the padded C1 table)
+  G16_CUDA(cudaEventRecord(ev_[5], st_[1]));
+  if (nv) sortW_.run(w + v_lo_, false, gw_, st_[1]);
+  G16_CUDA(cudaEventRecord(ev_[6], st_[1]));
+  G16_CUDA(cudaStreamWaitEvent(st_[2], ev_[6], 0));
+  if (nv) {
+    MsmPointSet<Fp> ws[3];
+    ws[0].points = tabA1_.as<G1Affine>();
+    ws[0].result = &res->a1;
+    ws[1].points = tabB1_.as<G1Affine>();
+    ws[1].result = &res->b1;
+    ws[2].points = tabC1_.as<G1Affine>();
+    ws[2].result = &res->c1;
+    accW_.run(sortW_, ws, 3, st_[1]);
+  }
+  G16_CUDA(cudaEventRecord(ev_[7], st_[1]));
+
+  // stream 2: pi_B MSM in G2 over the same sorted pairs (prover.nim:294)
+  G16_CUDA(cudaEventRecord(ev_[8], st_[2]));
+  if (nv) {
+    MsmPointSet<Fp2> bs;
+    bs.points = tabB2_.as<G2Affine>();
+    bs.result = &res->b2;
+    accB2_.run(sortW_, &bs, 1, st_[2]);
+  }
+  G16_CUDA(cudaEventRecord(ev_[9], st_[2]));
+
+  for (int i = 0; i < 3; i++) {
     G16_CUDA(cudaEventRecord(ev_[13 + i], st_[i]));
     G16_CUDA(cudaStreamWaitEvent(main_, ev_[13 + i], 0));
   }
@@ -309,10 +368,9 @@ void Prover::run_msms(g16_stats* stats) {
     cudaEventElapsedTime(&stats->ms_abc, ev_[1], ev_[2]);
     cudaEventElapsedTime(&stats->ms_quotient, ev_[2], ev_[3]);
     cudaEventElapsedTime(&stats->ms_msm_h, ev_[3], ev_[4]);
-    cudaEventElapsedTime(&stats->ms_msm_a, ev_[5], ev_[6]);
-    cudaEventElapsedTime(&stats->ms_msm_b1, ev_[7], ev_[8]);
-    cudaEventElapsedTime(&stats->ms_msm_b2, ev_[9], ev_[10]);
-    cudaEventElapsedTime(&stats->ms_msm_c, ev_[11], ev_[12]);
+    cudaEventElapsedTime(&stats->ms_sort_witness, ev_[5], ev_[6]);
+    cudaEventElapsedTime(&stats->ms_msm_g1_witness, ev_[6], ev_[7]);
+    cudaEventElapsedTime(&stats->ms_msm_b2, ev_[8], ev_[9]);
     cudaEventElapsedTime(&stats->ms_h2d, ev_[20], ev_[21]);
   }
 }

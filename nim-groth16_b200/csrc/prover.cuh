@@ -50,22 +50,25 @@ class Prover {
   void sync();
   void timer_start();                 // CUDA event on the context's main stream
   float timer_stop();                 // records, synchronises, returns elapsed ms since timer_start()
+  size_t resident_bytes() const;
 
  private:
   int shard_index_, shard_count_;
   uint32_t nvars_, npubs_, log_n_, flavour_;
   size_t n_;
-  size_t v_lo_, v_hi_, c_lo_, c_hi_, h_lo_, h_hi_;
-  DevBuf ptsA1_, ptsB1_, ptsB2_, ptsC1_, ptsH1_;
+  size_t v_lo_, v_hi_, h_lo_, h_hi_;
+  // resident window tables (2^(c w) P_i): A1, B1, C1 (padded to witness indices), H1 in G1; B2 in G2
+  DevBuf tabA1_, tabB1_, tabC1_, tabH1_, tabB2_;
+  MsmGeometry gw_, gh_;
+  MsmSorter sortW_, sortH_;
+  MsmAccumulator<Fp> accW_, accH_;
+  MsmAccumulator<Fp2> accB2_;
   SparseCsr csr_;
   DevBuf spec_, witness_, staging_, abc_, qs_, results_, mask_, proof_;
-  Msm<Fp> msmA_, msmB1_, msmH_, msmC_;
-  Msm<Fp2> msmB2_;
-  cudaStream_t main_ = nullptr, st_mask_ = nullptr, st_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t main_ = nullptr, st_mask_ = nullptr, st_[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_[24];
   cudaEvent_t tev_[2] = {nullptr, nullptr};
   g16_proof* proof_pinned_ = nullptr;
-  float ms_h2d_ = 0.f;
 };
 
 }  // namespace g16

@@ -30,13 +30,13 @@ class ProofRaw(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("ms_h2d", C.c_float), ("ms_abc", C.c_float), ("ms_quotient", C.c_float), ("ms_msm_a", C.c_float),
-                ("ms_msm_b1", C.c_float), ("ms_msm_b2", C.c_float), ("ms_msm_h", C.c_float),
-                ("ms_msm_c", C.c_float), ("ms_assemble", C.c_float), ("ms_total", C.c_float),
-                ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+    _fields_ = [("ms_h2d", C.c_float), ("ms_abc", C.c_float), ("ms_quotient", C.c_float),
+                ("ms_sort_witness", C.c_float), ("ms_msm_g1_witness", C.c_float), ("ms_msm_b2", C.c_float),
+                ("ms_msm_h", C.c_float), ("reserved_ms", C.c_float), ("ms_assemble", C.c_float),
+                ("ms_total", C.c_float), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
 
 
 class R1csView(C.Structure):
@@ -76,10 +76,13 @@ SIGNATURES = {
     "g16_prove_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ProofRaw),
                                 C.POINTER(Stats)]),
     "g16_prove_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]),
+    "g16_ctx_last_partials": (C.c_int, [C.c_void_p, C.c_void_p]),
     "g16_prove_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(ProofRaw)]),
     "g16_msm_plan_create": (C.c_int, [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
     "g16_msm_plan_destroy": (None, [C.c_void_p]),
     "g16_msm_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "g16_msm_plan_build_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "g16_msm_dev_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]),
     "g16_msm_result_to_affine": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "g16_msm_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "g16_msm_plan_profile": (C.c_int, [C.c_void_p, C.c_int]),

@@ -204,3 +204,41 @@ def test_msm_closed_form_large(g, lg, g2):
         else:
             got = g.msm_multi_threaded_g1(0, sc, pts, form=E.FORM_STD)
             assert E.g1_from_array(got)[0] == o.g1_mul(tot, o.GEN1)
+
+
+@pytest.mark.parametrize("lg,g2", [(10, False), (16, False), (10, True), (14, True)])
+def test_msm_resident_table_layout(g, lg, g2):
+    """The resident-key layout (window tables 2^(cw) P_i, one bucket set) against the closed form and the
+    plain layout, uniform and skewed scalars, through g16_msm_plan_build_table / g16_msm_dev_table."""
+    import ctypes as C
+    import torch
+    E = enc()
+    lib = g._lib.load()
+    n = 1 << lg
+    dl = E.random_fr_std(n, seed=15)
+    pts = g.fixed_base_g2(dl) if g2 else g.fixed_base_g1(dl)
+    pts[3] = 0                                             # a point at infinity inside the table
+    dl_i = E.fr_from_std(dl)
+    dl_i[3] = 0
+    d_pts = torch.from_numpy(pts.view(np.int64).copy()).to("cuda")
+    plan = C.c_void_p()
+    g._lib.check(lib.g16_msm_plan_create(1 if g2 else 0, n, 0, C.byref(plan)))
+    g._lib.check(lib.g16_msm_plan_build_table(plan, d_pts.data_ptr(), n, None))
+    res = torch.zeros(64, dtype=torch.int64, device="cuda")
+    for dist in ("uniform", "skewed"):
+        sc = E.random_fr_std(n, seed=14)
+        if dist == "skewed":
+            sc[: n // 2] = np.array([1, 0, 0, 0], np.uint64)      # half of the scalars equal 1: one giant bucket
+            sc[n // 2: n // 2 + n // 4] = 0
+        d_sc = torch.from_numpy(sc.view(np.int64).copy()).to("cuda")
+        g._lib.check(lib.g16_msm_dev_table(plan, d_sc.data_ptr(), 1, n, res.data_ptr(), None))
+        out = np.zeros(16 if g2 else 8, dtype=np.uint64)
+        g._lib.check(lib.g16_msm_result_to_affine(1 if g2 else 0, res.data_ptr(), 1, out.ctypes.data))
+        tot = sum(a * b for a, b in zip(E.fr_from_std(sc), dl_i)) % o.R
+        if g2:
+            assert E.g2_from_array(out)[0] == o.g2_mul(tot, o.GEN2)
+        else:
+            assert E.g1_from_array(out)[0] == o.g1_mul(tot, o.GEN1)
+        plain = (g.msm_multi_threaded_g2 if g2 else g.msm_multi_threaded_g1)(0, sc, pts, form=E.FORM_STD)
+        assert np.array_equal(plain, out)
+    lib.g16_msm_plan_destroy(plan)

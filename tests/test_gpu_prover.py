@@ -154,8 +154,22 @@ def _closed_form_proof(g, neqs, flav, seed):
                          e.fr_from_std(sc.h))
     cf = o.closed_form_proof_scalars(sco, tox_o, zk.npubs, w_i, qs_i, r, s)
     assert o.closed_form_check(sco, tox_o, zk.npubs, w_i, cf), "verifier equation fails in the exponent"
+    ok_b = e.g2_from_array(prf.pi_b)[0] == o.g2_mul(cf["b"], o.GEN2)
+    if not ok_b:      # localise: points, plain MSM, resident-table MSM or the mask term
+        import random as _r
+        idx = _r.Random(1).sample(range(zk.nvars), 5)
+        pts_ok = all(e.g2_from_array(zk.pointsB2[j:j + 1])[0] == o.g2_mul(sco.b[j], o.GEN2) for j in idx)
+        plain = e.g2_from_array(g.msm_multi_threaded_g2(0, wit, zk.pointsB2, form=e.FORM_STD))[0]
+        plain_ok = plain == o.g2_mul(cf["msmB"], o.GEN2)
+        ctx0 = g.ProverContext(zk)
+        p0 = ctx0.prove(wit, g.Mask(0, 0))
+        p1 = ctx0.prove(wit, g.Mask(r, s))
+        ctx0.close()
+        b0_ok = e.g2_from_array(p0.pi_b)[0] == o.g2_mul((tox_o.beta + cf["msmB"]) % o.R, o.GEN2)
+        b1_ok = e.g2_from_array(p1.pi_b)[0] == o.g2_mul(cf["b"], o.GEN2)
+        raise AssertionError("pi_b mismatch: B2 points ok=%s, plain MSM ok=%s, fresh ctx trivial mask ok=%s, "
+                             "fresh ctx same mask ok=%s" % (pts_ok, plain_ok, b0_ok, b1_ok))
     assert e.g1_from_array(prf.pi_a)[0] == o.g1_mul(cf["a"], o.GEN1)
-    assert e.g2_from_array(prf.pi_b)[0] == o.g2_mul(cf["b"], o.GEN2)
     assert e.g1_from_array(prf.pi_c)[0] == o.g1_mul(cf["c"], o.GEN1)
     return zk, wit, prf, stats
 
@@ -219,4 +233,26 @@ def test_sharded_contexts_recombine_on_one_gpu(g, kat):
         for c in ctxs:
             c.close()
         assert np.array_equal(got.pi_a, want.pi_a) and np.array_equal(got.pi_b, want.pi_b)
+        assert np.array_equal(got.pi_c, want.pi_c)
+
+
+def test_context_creation_is_stream_ordered_under_dirty_memory(g):
+    """Regression: uploads at g16_ctx_create must be ordered before the table-building kernels on the library's
+    non-blocking streams.  Recycled (dirty) device memory made a late DMA visible as a wrong G2 MSM."""
+    import torch
+    e = E()
+    r1cs, wit = g.synthetic_chain_circuit(5000, seed=3)
+    tox = g.ToxicWaste(101, 202, 303, 404, 505)
+    zk, _ = g.fake_circuit_setup(r1cs, tox, 1)
+    m = g.Mask(o.Rng(3).fr(), o.Rng(4).fr())
+    ctx = g.ProverContext(zk)
+    want = ctx.prove(wit, m)
+    ctx.close()
+    for rep in range(25):
+        junk = torch.randint(0, 255, (rep * 1000003 % 7000000 + 10,), dtype=torch.uint8, device="cuda")
+        del junk
+        ctx = g.ProverContext(zk)
+        got = ctx.prove(wit, m)
+        ctx.close()
+        assert np.array_equal(got.pi_b, want.pi_b) and np.array_equal(got.pi_a, want.pi_a)
         assert np.array_equal(got.pi_c, want.pi_c)

@@ -36,7 +36,14 @@ for g2 in (0, 1):
     for i in range(2):
         _lib.check(lib.g16_msm_dev(plan, w.data_ptr(), 1, pts.data_ptr(), n, res.data_ptr(), None))
         _lib.check(lib.g16_msm_plan_last_profile(plan, C.byref(a), C.byref(t), C.byref(p)))
-        print("msm g%d: total %.3f ms, accumulate %.3f ms, pairs %d" % (g2 + 1, t.value, a.value, p.value), flush=True)
+        print("msm g%d plain: total %.3f ms, accumulate %.3f ms, pairs %d" % (g2 + 1, t.value, a.value, p.value), flush=True)
+    t0 = time.perf_counter()
+    _lib.check(lib.g16_msm_plan_build_table(plan, pts.data_ptr(), n, None))
+    print("table build g%d: %.1f ms" % (g2 + 1, (time.perf_counter() - t0) * 1e3), flush=True)
+    for i in range(2):
+        _lib.check(lib.g16_msm_dev_table(plan, w.data_ptr(), 1, n, res.data_ptr(), None))
+        _lib.check(lib.g16_msm_plan_last_profile(plan, C.byref(a), C.byref(t), C.byref(p)))
+        print("msm g%d table: total %.3f ms, accumulate %.3f ms, pairs %d" % (g2 + 1, t.value, a.value, p.value), flush=True)
     lib.g16_msm_plan_destroy(plan)
 x = torch.from_numpy(g.encoding.random_fr_std(1 << log_n, 6).view(np.int64)).to("cuda")
 y = torch.empty_like(x)
