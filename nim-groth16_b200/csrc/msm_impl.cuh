@@ -8,8 +8,8 @@
 //   k_bucket_accumulate  one thread per work item (<= T mixed additions, items sorted by length), gathered
 //                        affine loads (16-byte vectors), XYZZ accumulator in registers
 //   k_bucket_fixup       buckets that were split into several items: block-wide tree sum of their partials
-//   k_bucket_reduce      sum_k (k+1) B_k per bucket set: segmented running sums + block tree reduction
-//   k_window_combine     plain layout: Horner over the windows;  k_final_sum: precomputed layout: tree sum
+//   k_reduce_level/final sum_k (k+1) B_k per bucket set as a recursion over levels of running sums
+//   k_window_combine     Horner over the windows (plain layout; a single window in the precomputed layout)
 //   k_build_table        precomputed layout: 2^(c w) P_i for every window, batch-normalised to affine
 #pragma once
 #include "msm.cuh"
@@ -122,28 +122,40 @@ __global__ void __launch_bounds__(128) k_bucket_fixup(AccSets<F> sets, const uin
 }
 
 // ---------------------------------------------------------------------------------------
-// bucket reduction: per bucket set, sum_k (k+1) * B_k
-//    thread t owns buckets [t*L, (t+1)*L): running sums give S_t = sum B_k and
-//    R_t = sum (k - t*L + 1) B_k; its contribution is R_t + (t*L) * S_t.
-// grid = (blocks per bucket set, bucket sets (windows), point sets)
+// bucket reduction: per bucket set, sum_k (k+1) * B_k, as a recursion over levels.
+//   level 1: thread t owns L consecutive buckets; running sums give S_t = sum_j B_{tL+j} and
+//            R_t = sum_j (j+1) B_{tL+j}.  Then sum_k (k+1) B_k = sum_t R_t + L * sum_t t * S_t,
+//   and sum_t t * S_t is the same problem on the L-times shorter array S with 0-based weights (level 2, ...).
+//   Result = R^(1) + L * (R^(2) + L * (R^(3) + ...)),  R^(l) = plain sum of the level's local weighted sums.
+// No per-thread scalar multiplication; each level is one launch and the tiny upper levels overlap with the
+// other streams' work.   grid = (blocks, bucket sets (windows), point sets)
 // ---------------------------------------------------------------------------------------
 template <class F>
-__global__ void __launch_bounds__(128) k_bucket_reduce(AccSets<F> sets, uint32_t nb, uint32_t L) {
+struct ReduceLevel {
+  const XYZZ<F>* in[MsmAccumulator<F>::MAX_SETS];    // n_in entries per bucket set
+  XYZZ<F>* out_s[MsmAccumulator<F>::MAX_SETS];       // n_in / L entries per bucket set (input of the next level)
+  XYZZ<F>* out_r[MsmAccumulator<F>::MAX_SETS];       // gridDim.x block sums of R per bucket set
+  uint32_t n_in, L;
+  int weight_one_based;                              // level 1: weights j+1; upper levels: weights j
+};
+
+template <class F>
+__global__ void __launch_bounds__(128) k_reduce_level(ReduceLevel<F> a) {
   extern __shared__ uint4 red_raw[];
   XYZZ<F>* red = reinterpret_cast<XYZZ<F>*>(red_raw);
   const uint32_t w = blockIdx.y;
   const int set = blockIdx.z;
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;     // segment index inside the bucket set
-  const XYZZ<F>* B = sets.buckets[set] + (size_t)w * nb + (size_t)t * L;
+  const uint32_t nthreads = a.n_in / a.L;                       // per bucket set
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   XYZZ<F> running = xyzz_inf<F>(), sum = xyzz_inf<F>();
-  for (int k = (int)L - 1; k >= 0; k--) {
-    XYZZ<F> b = ld_vec(B + k);
-    xyzz_add_ni(running, running, b);
-    xyzz_add_ni(sum, sum, running);
-  }
-  if (t) {
-    XYZZ<F> off = xyzz_mul_u32(t * L, running);
-    xyzz_add_ni(sum, sum, off);
+  if (t < nthreads) {
+    const XYZZ<F>* B = a.in[set] + (size_t)w * a.n_in + (size_t)t * a.L;
+    for (int k = (int)a.L - 1; k >= 0; k--) {
+      XYZZ<F> b = ld_vec(B + k);
+      xyzz_add_ni(running, running, b);
+      if (k > 0 || a.weight_one_based) xyzz_add_ni(sum, sum, running);
+    }
+    st_vec(a.out_s[set] + (size_t)w * nthreads + t, running);
   }
   red[threadIdx.x] = sum;
   __syncthreads();
@@ -155,59 +167,68 @@ __global__ void __launch_bounds__(128) k_bucket_reduce(AccSets<F> sets, uint32_t
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) st_vec(sets.winpart[set] + (size_t)w * gridDim.x + blockIdx.x, sum);
+  if (threadIdx.x == 0) st_vec(a.out_r[set] + (size_t)w * gridDim.x + blockIdx.x, sum);
 }
 
-// plain layout: result = sum_w 2^(c w) * W_w  (Horner from the top window); grid.x = point sets
+constexpr int MSM_MAX_LEVELS = 8;
 template <class F>
-__global__ void k_window_combine(AccSets<F> sets, uint32_t bpw, int nwin, int c) {
-  extern __shared__ uint4 red_raw[];
-  XYZZ<F>* win = reinterpret_cast<XYZZ<F>*>(red_raw);
-  const int set = blockIdx.x;
-  int w = threadIdx.x;
-  if (w < nwin) {
-    XYZZ<F> acc = xyzz_inf<F>();
-    for (uint32_t i = 0; i < bpw; i++) {
-      XYZZ<F> o = ld_vec(sets.winpart[set] + (size_t)w * bpw + i);
-      xyzz_add_ni(acc, acc, o);
-    }
-    win[w] = acc;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    XYZZ<F> acc = win[nwin - 1];
-    for (int i = nwin - 2; i >= 0; i--) {
-      for (int j = 0; j < c; j++) xyzz_dbl_ni(acc, acc);
-      XYZZ<F> o = win[i];
-      xyzz_add_ni(acc, acc, o);
-    }
-    st_vec(sets.result[set], acc);
-  }
-}
+struct ReduceFinal {
+  const XYZZ<F>* r[MsmAccumulator<F>::MAX_SETS][MSM_MAX_LEVELS];   // block sums of each level
+  XYZZ<F>* wintot[MsmAccumulator<F>::MAX_SETS];                    // one total per bucket set (window)
+  uint32_t blocks[MSM_MAX_LEVELS];
+  uint32_t logL[MSM_MAX_LEVELS];
+  int nlevels;
+};
 
-// precomputed layout: result = tree sum of the `count` block partials; grid.x = point sets
+// total of one bucket set: Horner over the levels; grid = (bucket sets, point sets), 128 threads
 template <class F>
-__global__ void __launch_bounds__(128) k_final_sum(AccSets<F> sets, uint32_t count) {
+__global__ void __launch_bounds__(128) k_reduce_final(ReduceFinal<F> a) {
   extern __shared__ uint4 red_raw[];
   XYZZ<F>* red = reinterpret_cast<XYZZ<F>*>(red_raw);
-  const int set = blockIdx.x;
-  XYZZ<F> acc = xyzz_inf<F>();
-  for (uint32_t k = threadIdx.x; k < count; k += blockDim.x) {
-    XYZZ<F> o = ld_vec(sets.winpart[set] + k);
-    xyzz_add_ni(acc, acc, o);
-  }
-  red[threadIdx.x] = acc;
-  __syncthreads();
-  for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
-    if (threadIdx.x < s) {
-      XYZZ<F> o = red[threadIdx.x + s];
+  const uint32_t w = blockIdx.x;
+  const int set = blockIdx.y;
+  XYZZ<F> total = xyzz_inf<F>();          // only meaningful in thread 0
+  for (int l = a.nlevels - 1; l >= 0; l--) {
+    XYZZ<F> acc = xyzz_inf<F>();
+    for (uint32_t k = threadIdx.x; k < a.blocks[l]; k += blockDim.x) {
+      XYZZ<F> o = ld_vec(a.r[set][l] + (size_t)w * a.blocks[l] + k);
       xyzz_add_ni(acc, acc, o);
-      red[threadIdx.x] = acc;
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+      if (threadIdx.x < s) {
+        XYZZ<F> o = red[threadIdx.x + s];
+        xyzz_add_ni(acc, acc, o);
+        red[threadIdx.x] = acc;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      // total = R^(l) + L_l * total   (the levels above act through the weights of this level)
+      for (uint32_t j = 0; j < a.logL[l]; j++) xyzz_dbl_ni(total, total);
+      xyzz_add_ni(total, total, acc);
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) st_vec(sets.result[set], acc);
+  if (threadIdx.x == 0) st_vec(a.wintot[set] + w, total);
 }
+
+// result = sum_w 2^(c w) * W_w  (Horner from the top window; one window in the precomputed layout)
+// grid.x = point sets; sets.winpart[] points at the window totals
+template <class F>
+__global__ void k_window_combine(AccSets<F> sets, int nwin, int c) {
+  if (threadIdx.x != 0) return;
+  const int set = blockIdx.x;
+  XYZZ<F> acc = ld_vec(sets.winpart[set] + (nwin - 1));
+  for (int i = nwin - 2; i >= 0; i--) {
+    for (int j = 0; j < c; j++) xyzz_dbl_ni(acc, acc);
+    XYZZ<F> o = ld_vec(sets.winpart[set] + i);
+    xyzz_add_ni(acc, acc, o);
+  }
+  st_vec(sets.result[set], acc);
+}
+
 
 template <class F>
 __global__ void k_set_inf(XYZZ<F>* p) {
@@ -310,16 +331,31 @@ void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, i
   G16_REQUIRE(nsets >= 1 && nsets <= MAX_SETS, "MsmAccumulator: 1..3 point sets");
   const MsmGeometry& g = sorter.geom();
   G16_REQUIRE(g.nwin <= MSM_MAX_WINDOWS, "too many windows");
-  // reduction geometry: segments of L buckets, 128 segments per block
-  uint32_t L = g.nb < 16u ? 1u : 16u;
-  uint32_t nseg = g.nb / L;
-  uint32_t tpb = nseg < 128u ? nseg : 128u;
-  uint32_t bpw = nseg / tpb;                       // blocks (partial sums) per bucket set
-  uint32_t nsetsB = g.precomp ? 1u : (uint32_t)g.nwin;
+  // reduction levels: n_0 = nb buckets; level l maps n_l entries to n_l / L_l entries, down to one
+  const uint32_t nsetsB = g.precomp ? 1u : (uint32_t)g.nwin;
+  int nlevels = 0;
+  uint32_t lvl_n[MSM_MAX_LEVELS + 1], lvl_L[MSM_MAX_LEVELS], lvl_tpb[MSM_MAX_LEVELS], lvl_blocks[MSM_MAX_LEVELS];
+  lvl_n[0] = g.nb;
+  while (lvl_n[nlevels] > 1) {
+    G16_REQUIRE(nlevels < MSM_MAX_LEVELS, "too many reduction levels");
+    uint32_t L = lvl_n[nlevels] >= 16u ? 16u : lvl_n[nlevels];
+    uint32_t threads = lvl_n[nlevels] / L;
+    lvl_L[nlevels] = L;
+    lvl_tpb[nlevels] = threads < 128u ? (threads < 32u ? 32u : threads) : 128u;
+    lvl_blocks[nlevels] = (threads + lvl_tpb[nlevels] - 1) / lvl_tpb[nlevels];
+    lvl_n[nlevels + 1] = threads;
+    nlevels++;
+  }
+  // scratch per point set: the S array and the block sums of every level, then one total per bucket set
+  size_t s_entries = 0, r_entries = 0;
+  for (int l = 0; l < nlevels; l++) {
+    s_entries += (size_t)nsetsB * lvl_n[l + 1];
+    r_entries += (size_t)nsetsB * lvl_blocks[l];
+  }
 
   size_t bucket_bytes = (size_t)g.nbuckets * sizeof(XYZZ<F>);
   size_t partial_bytes = (size_t)g.max_items * sizeof(XYZZ<F>);
-  size_t winpart_bytes = (size_t)nsetsB * bpw * sizeof(XYZZ<F>);
+  size_t winpart_bytes = (s_entries + r_entries + nsetsB) * sizeof(XYZZ<F>);
   buckets_.ensure(bucket_bytes * nsets);
   partials_.ensure(partial_bytes * nsets);
   winpart_.ensure(winpart_bytes * nsets);
@@ -349,15 +385,45 @@ void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, i
   k_bucket_fixup<F><<<fgrid, 128, 128 * sizeof(XYZZ<F>), stream>>>(sets, sorter.item_start(), sorter.multi_count(),
                                                                    sorter.multi_list());
   G16_LAUNCH_CHECK();
-  dim3 rgrid(bpw, nsetsB, (unsigned)nsets);
-  k_bucket_reduce<F><<<rgrid, tpb, tpb * sizeof(XYZZ<F>), stream>>>(sets, g.nb, L);
-  G16_LAUNCH_CHECK();
-  if (g.precomp) {
-    k_final_sum<F><<<nsets, 128, 128 * sizeof(XYZZ<F>), stream>>>(sets, bpw);
-  } else {
-    int cthreads = ((g.nwin + 31) / 32) * 32;
-    k_window_combine<F><<<nsets, cthreads, (size_t)g.nwin * sizeof(XYZZ<F>), stream>>>(sets, bpw, g.nwin, g.c);
+  // bucket reduction: one launch per level, then the per-set Horner over the levels
+  ReduceFinal<F> fin;
+  fin.nlevels = nlevels;
+  size_t off_s = 0, off_r = s_entries;
+  const size_t off_t = s_entries + r_entries;
+  for (int l = 0; l < nlevels; l++) {
+    ReduceLevel<F> lv;
+    lv.n_in = lvl_n[l];
+    lv.L = lvl_L[l];
+    lv.weight_one_based = (l == 0) ? 1 : 0;
+    for (int s = 0; s < MAX_SETS; s++) {
+      XYZZ<F>* base = sets.winpart[s];
+      lv.in[s] = (l == 0) ? sets.buckets[s] : base + (off_s - (size_t)nsetsB * lvl_n[l]);
+      lv.out_s[s] = base + off_s;
+      lv.out_r[s] = base + off_r;
+      fin.r[s][l] = base + off_r;
+      fin.wintot[s] = base + off_t;
+    }
+    fin.blocks[l] = lvl_blocks[l];
+    uint32_t lg = 0;
+    while ((1u << lg) < lvl_L[l]) lg++;
+    fin.logL[l] = lg;
+    dim3 rgrid(lvl_blocks[l], nsetsB, (unsigned)nsets);
+    k_reduce_level<F><<<rgrid, lvl_tpb[l], lvl_tpb[l] * sizeof(XYZZ<F>), stream>>>(lv);
+    G16_LAUNCH_CHECK();
+    off_s += (size_t)nsetsB * lvl_n[l + 1];
+    off_r += (size_t)nsetsB * lvl_blocks[l];
   }
+  for (int l = nlevels; l < MSM_MAX_LEVELS; l++) {
+    fin.blocks[l] = 0;
+    fin.logL[l] = 0;
+    for (int s = 0; s < MAX_SETS; s++) fin.r[s][l] = nullptr;
+  }
+  dim3 fgrid2(nsetsB, (unsigned)nsets);
+  k_reduce_final<F><<<fgrid2, 128, 128 * sizeof(XYZZ<F>), stream>>>(fin);
+  G16_LAUNCH_CHECK();
+  AccSets<F> wsets = sets;
+  for (int s = 0; s < MAX_SETS; s++) wsets.winpart[s] = sets.winpart[s] + off_t;
+  k_window_combine<F><<<nsets, 32, 0, stream>>>(wsets, g.precomp ? 1 : g.nwin, g.c);
   G16_LAUNCH_CHECK();
 }
 

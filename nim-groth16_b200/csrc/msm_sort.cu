@@ -47,9 +47,13 @@ MsmGeometry msm_geometry(size_t n, int c, bool precomp) {
   g.nbuckets = precomp ? g.nb : (uint32_t)g.nwin * g.nb;
   g.m = (size_t)g.nwin * n;
   G16_REQUIRE(g.m < ((size_t)1 << 31), "MSM pair count must fit 31 bits");
+  // a work item is at most T additions.  Items are sorted by length, so T only has to bound the tail of a
+  // launch, not balance lanes; it is kept well above the heaviest regular bucket (the top window of a 254-bit
+  // scalar has few significant bits, which makes the low buckets several times heavier than the average) and
+  // only splits the giant buckets of skewed scalar distributions (many 0/1/small witness values).
   size_t avg = g.m / g.nbuckets + 1;
-  size_t T = 4 * avg;
-  if (T < 64) T = 64;
+  size_t T = 16 * avg;
+  if (T < 256) T = 256;
   if (T > 32768) T = 32768;
   g.T = (uint32_t)T;
   g.max_items = g.nbuckets + (uint32_t)(g.m / T) + 1;

@@ -46,36 +46,91 @@ static __device__ void neg_rs(const uint32_t r[8], const uint32_t s[8], uint32_t
   for (int i = 0; i < 8; i++) out[i] = p.v[i];
 }
 
-// mask terms that do not depend on any MSM; warps 0..3 work independently (lane 0 only)
-__global__ void __launch_bounds__(128) k_mask_terms(const SpecPointsDev* spec, MaskTerms* m) {
+// Tables 2^j * delta1 (G1) and 2^j * delta2 (G2), j < 256, built once per context: the mask terms
+// r ** delta1, s ** delta1, negFr(r*s) ** delta1, s ** delta2 (prover.nim:281,287,293,300) then need no
+// doubling chain -- a block adds the table entries selected by the scalar's bits in a tree.
+__global__ void k_delta_tables(const SpecPointsDev* spec, G1XYZZ* t1, G2XYZZ* t2) {
   if (threadIdx.x & 31) return;
-  int w = threadIdx.x >> 5;
-  if (w == 0) {                                       // alpha1 + r ** delta1      prover.nim:280-281
-    G1XYZZ t = xyzz_scalar_mul(m->r, ldv(&spec->delta1));
-    xyzz_madd_ni(t, t, ldv(&spec->alpha1));
-    stv(&m->t_a, t);
-  } else if (w == 1) {                                // beta1 + s ** delta1       prover.nim:286-287
-    G1XYZZ t = xyzz_scalar_mul(m->s, ldv(&spec->delta1));
-    xyzz_madd_ni(t, t, ldv(&spec->beta1));
-    stv(&m->t_b1, t);
-  } else if (w == 2) {                                // beta2 + s ** delta2       prover.nim:292-293
-    G2XYZZ t = xyzz_scalar_mul(m->s, ldv(&spec->delta2));
-    xyzz_madd_ni(t, t, ldv(&spec->beta2));
-    stv(&m->t_b2, t);
-  } else {                                            // negFr(r*s) ** delta1      prover.nim:300
-    uint32_t k[8];
-    neg_rs(m->r, m->s, k);
-    G1XYZZ t = xyzz_scalar_mul(k, ldv(&spec->delta1));
-    stv(&m->t_c, t);
+  if ((threadIdx.x >> 5) == 0) {
+    G1XYZZ p = xyzz_from_affine(ldv(&spec->delta1));
+    for (int j = 0; j < 256; j++) {
+      stv(t1 + j, p);
+      xyzz_dbl_ni(p, p);
+    }
+  } else {
+    G2XYZZ p = xyzz_from_affine(ldv(&spec->delta2));
+    for (int j = 0; j < 256; j++) {
+      stv(t2 + j, p);
+      xyzz_dbl_ni(p, p);
+    }
   }
 }
 
-// proof assembly, prover.nim:278-304
-__global__ void __launch_bounds__(128) k_assemble(const MsmResults* res, const MaskTerms* m, g16_proof* proof) {
-  __shared__ G1XYZZ sh[3];
+template <class F>
+static __device__ void block_bits_sum(const uint32_t k[8], const XYZZ<F>* table, XYZZ<F>* red, XYZZ<F>& out) {
+  const uint32_t j = threadIdx.x;                    // 256 threads, one per scalar bit
+  XYZZ<F> acc = xyzz_inf<F>();
+  if ((k[j >> 5] >> (j & 31)) & 1u) acc = ldv(table + j);
+  red[j] = acc;
+  __syncthreads();
+  for (uint32_t s = 128; s > 0; s >>= 1) {
+    if (j < s) {
+      XYZZ<F> o = red[j + s];
+      xyzz_add_ni(acc, acc, o);
+      red[j] = acc;
+    }
+    __syncthreads();
+  }
+  out = acc;
+}
+
+// blocks 0..2: G1 terms; block 3: the G2 term.  256 threads per block.
+__global__ void __launch_bounds__(256) k_mask_terms(const SpecPointsDev* spec, const G1XYZZ* t1, const G2XYZZ* t2,
+                                                    MaskTerms* m) {
+  extern __shared__ uint4 red_raw[];
+  __shared__ uint32_t k[8];
+  const int term = blockIdx.x;
+  if (threadIdx.x == 0) {
+    if (term == 2) neg_rs(m->r, m->s, k);             // negFr(r*s)                 prover.nim:300
+    else
+      for (int i = 0; i < 8; i++) k[i] = (term == 0) ? m->r[i] : m->s[i];
+  }
+  __syncthreads();
+  if (term < 3) {
+    G1XYZZ* red = reinterpret_cast<G1XYZZ*>(red_raw);
+    G1XYZZ acc;
+    block_bits_sum<Fp>(k, t1, red, acc);
+    if (threadIdx.x == 0) {
+      if (term == 0) {                                // alpha1 + r ** delta1       prover.nim:280-281
+        xyzz_madd_ni(acc, acc, ldv(&spec->alpha1));
+        stv(&m->t_a, acc);
+      } else if (term == 1) {                         // beta1 + s ** delta1        prover.nim:286-287
+        xyzz_madd_ni(acc, acc, ldv(&spec->beta1));
+        stv(&m->t_b1, acc);
+      } else {
+        stv(&m->t_c, acc);
+      }
+    }
+  } else {
+    G2XYZZ* red = reinterpret_cast<G2XYZZ*>(red_raw);
+    G2XYZZ acc;
+    block_bits_sum<Fp2>(k, t2, red, acc);
+    if (threadIdx.x == 0) {                           // beta2 + s ** delta2        prover.nim:292-293
+      xyzz_madd_ni(acc, acc, ldv(&spec->beta2));
+      stv(&m->t_b2, acc);
+    }
+  }
+}
+
+// proof assembly, prover.nim:278-304, in two kernels so that the expensive half overlaps with the MSMs that
+// finish later.
+// early (needs only the G1 witness MSMs A1, B1, C1): pi_a, rho, s ** pi_a, r ** rho and
+//   partial_c = s**pi_a + r**rho + (-rs)**delta1 + MSM(zs, C1)
+__global__ void __launch_bounds__(64) k_assemble_early(const MsmResults* res, const MaskTerms* m, g16_proof* proof,
+                                                       G1XYZZ* partial_c) {
+  __shared__ G1XYZZ sh[2];
   int w = threadIdx.x >> 5;
-  bool lead = (threadIdx.x & 31) == 0;
-  if (lead) {
+  if ((threadIdx.x & 31) == 0) {
     if (w == 0) {                                     // pi_a, then s ** pi_a       prover.nim:282,298
       G1XYZZ t;
       xyzz_add_ni(t, ldv(&m->t_a), ldv(&res->a1));
@@ -83,33 +138,40 @@ __global__ void __launch_bounds__(128) k_assemble(const MsmResults* res, const M
       xyzz_to_affine_ni(pa, t);
       stv(reinterpret_cast<G1Affine*>(proof->pi_a), pa);
       sh[0] = xyzz_scalar_mul(m->s, pa);
-    } else if (w == 1) {                              // rho, then r ** rho         prover.nim:288,299
+    } else {                                          // rho, then r ** rho         prover.nim:288,299
       G1XYZZ t;
       xyzz_add_ni(t, ldv(&m->t_b1), ldv(&res->b1));
       G1Affine rho;
       xyzz_to_affine_ni(rho, t);
       sh[1] = xyzz_scalar_mul(m->r, rho);
-    } else if (w == 2) {                              // pi_b                       prover.nim:294
-      G2XYZZ t;
-      xyzz_add_ni(t, ldv(&m->t_b2), ldv(&res->b2));
-      G2Affine pb;
-      xyzz_to_affine_ni(pb, t);
-      stv(reinterpret_cast<G2Affine*>(proof->pi_b), pb);
-    } else {                                          // -rs*delta1 + MSM(H) + MSM(C)   prover.nim:300-302
-      G1XYZZ t;
-      xyzz_add_ni(t, ldv(&m->t_c), ldv(&res->h1));
-      xyzz_add_ni(t, t, ldv(&res->c1));
-      sh[2] = t;
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) {                             // + negFr(r*s) ** delta1 + MSM(zs, C1)   prover.nim:300,302
     G1XYZZ t;
     xyzz_add_ni(t, sh[0], sh[1]);
-    xyzz_add_ni(t, t, sh[2]);
+    xyzz_add_ni(t, t, ldv(&m->t_c));
+    xyzz_add_ni(t, t, ldv(&res->c1));
+    stv(partial_c, t);
+  }
+}
+
+// final (needs B2 and H1): pi_b and pi_c
+__global__ void __launch_bounds__(64) k_assemble_final(const MsmResults* res, const MaskTerms* m,
+                                                       const G1XYZZ* partial_c, g16_proof* proof) {
+  if (threadIdx.x & 31) return;
+  if ((threadIdx.x >> 5) == 0) {                      // pi_c = partial_c + MSM(qs, H1)          prover.nim:301
+    G1XYZZ t;
+    xyzz_add_ni(t, ldv(partial_c), ldv(&res->h1));
     G1Affine pc;
     xyzz_to_affine_ni(pc, t);
     stv(reinterpret_cast<G1Affine*>(proof->pi_c), pc);
+  } else {                                            // pi_b                                     prover.nim:294
+    G2XYZZ t;
+    xyzz_add_ni(t, ldv(&m->t_b2), ldv(&res->b2));
+    G2Affine pb;
+    xyzz_to_affine_ni(pb, t);
+    stv(reinterpret_cast<G2Affine*>(proof->pi_b), pb);
   }
 }
 
@@ -240,6 +302,12 @@ Prover::Prover(const g16_zkey_view& zk, int shard_index, int shard_count)
   memcpy(&sp.delta2, zk.delta2, 128);
   spec_.ensure(sizeof(SpecPointsDev));
   G16_CUDA(cudaMemcpyAsync(spec_.p, &sp, sizeof(sp), cudaMemcpyHostToDevice, main_));
+  G16_CUDA(cudaFuncSetAttribute(k_mask_terms, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(256 * sizeof(G2XYZZ))));
+  dtab1_.ensure(256 * sizeof(G1XYZZ));
+  dtab2_.ensure(256 * sizeof(G2XYZZ));
+  k_delta_tables<<<1, 64, 0, main_>>>(spec_.as<SpecPointsDev>(), dtab1_.as<G1XYZZ>(), dtab2_.as<G2XYZZ>());
+  G16_LAUNCH_CHECK();
   G16_CUDA(cudaStreamSynchronize(main_));
 
   witness_.ensure((size_t)nvars_ * sizeof(Fr));
@@ -249,6 +317,7 @@ Prover::Prover(const g16_zkey_view& zk, int shard_index, int shard_count)
   G16_CUDA(cudaMemset(results_.p, 0, sizeof(MsmResults)));   // all-zero XYZZ == infinity (empty shards)
   mask_.ensure(sizeof(MaskTerms));
   proof_.ensure(sizeof(g16_proof));
+  early_.ensure(sizeof(G1XYZZ));
   G16_CUDA(cudaMallocHost(reinterpret_cast<void**>(&proof_pinned_), sizeof(g16_proof)));
   ntt_prepare((int)log_n_, main_);
   G16_CUDA(cudaStreamSynchronize(main_));
@@ -347,6 +416,14 @@ void Prover::run_msms(g16_stats* stats) {
     accW_.run(sortW_, ws, 3, st_[1]);
   }
   G16_CUDA(cudaEventRecord(ev_[7], st_[1]));
+  if (mask_started_ && shard_count_ == 1) {
+    // the MSM-dependent scalar multiplications start now and overlap with the B2 / H work still in flight
+    G16_CUDA(cudaStreamWaitEvent(st_[1], ev_[23], 0));
+    k_assemble_early<<<1, 64, 0, st_[1]>>>(results_.as<MsmResults>(), mask_.as<MaskTerms>(), proof_.as<g16_proof>(),
+                                           early_.as<G1XYZZ>());
+    G16_LAUNCH_CHECK();
+    early_done_ = true;
+  }
 
   // stream 2: pi_B MSM in G2 over the same sorted pairs (prover.nim:294)
   G16_CUDA(cudaEventRecord(ev_[8], st_[2]));
@@ -397,18 +474,28 @@ void Prover::start_mask(const uint64_t r[4], const uint64_t s[4]) {
   memcpy(rs + 8, s, 32);
   G16_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(m) + offsetof(MaskTerms, r), rs, 64, cudaMemcpyHostToDevice,
                            st_mask_));
-  k_mask_terms<<<1, 128, 0, st_mask_>>>(spec_.as<SpecPointsDev>(), m);
+  k_mask_terms<<<4, 256, 256 * sizeof(G2XYZZ), st_mask_>>>(spec_.as<SpecPointsDev>(), dtab1_.as<G1XYZZ>(),
+                                                           dtab2_.as<G2XYZZ>(), m);
   G16_LAUNCH_CHECK();
   G16_CUDA(cudaEventRecord(ev_[23], st_mask_));
+  mask_started_ = true;
+  early_done_ = false;
 }
 
 void Prover::finish(g16_proof* proof, g16_stats* stats) {
   G16_REQUIRE(proof != nullptr, "proof output is null");
+  G16_REQUIRE(mask_started_, "finish without start_mask");
   MaskTerms* m = mask_.as<MaskTerms>();
   G16_CUDA(cudaEventRecord(ev_[19], main_));
   G16_CUDA(cudaStreamWaitEvent(main_, ev_[23], 0));
-  k_assemble<<<1, 128, 0, main_>>>(results_.as<MsmResults>(), m, proof_.as<g16_proof>());
+  if (!early_done_) {                                  // multi-GPU path: the sums arrive only now
+    k_assemble_early<<<1, 64, 0, main_>>>(results_.as<MsmResults>(), m, proof_.as<g16_proof>(), early_.as<G1XYZZ>());
+    G16_LAUNCH_CHECK();
+  }
+  k_assemble_final<<<1, 64, 0, main_>>>(results_.as<MsmResults>(), m, early_.as<G1XYZZ>(), proof_.as<g16_proof>());
   G16_LAUNCH_CHECK();
+  mask_started_ = false;
+  early_done_ = false;
   G16_CUDA(cudaMemcpyAsync(proof_pinned_, proof_.p, sizeof(g16_proof), cudaMemcpyDeviceToHost, main_));
   G16_CUDA(cudaEventRecord(ev_[22], main_));
   G16_CUDA(cudaStreamSynchronize(main_));

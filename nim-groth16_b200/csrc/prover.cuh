@@ -64,7 +64,9 @@ class Prover {
   MsmAccumulator<Fp> accW_, accH_;
   MsmAccumulator<Fp2> accB2_;
   SparseCsr csr_;
-  DevBuf spec_, witness_, staging_, abc_, qs_, results_, mask_, proof_;
+  DevBuf dtab1_, dtab2_;   // 2^j * delta1 / delta2
+  DevBuf spec_, witness_, staging_, abc_, qs_, results_, mask_, proof_, early_;
+  bool mask_started_ = false, early_done_ = false;
   cudaStream_t main_ = nullptr, st_mask_ = nullptr, st_[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_[24];
   cudaEvent_t tev_[2] = {nullptr, nullptr};
