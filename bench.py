@@ -115,7 +115,7 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_cpu as oc
     import g16b200 as g
-    sl = args.sample_log_n
+    sl = min(args.sample_log_n, args.log_n)
     zk, wit, _ = make_fixture(g, sl)                       # fixture generation (GPU fake setup) is untimed
     cores = oc.ncpu()
     times = []
@@ -253,7 +253,7 @@ def run_ours(args):
         out.update(micro_benchmarks(args, g, lib, zk, w_dev, torch))
     if world == 1 and not args.no_cpu_baseline:
         try:
-            out["cpu_baseline"] = cpu_baseline(args, g)
+            out["cpu_baseline"] = cpu_baseline(args, g, zk, wit)
         except Exception as ex:      # the checker being unavailable must not kill the GPU number
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
                                    "sample": "failed: %r" % (ex,)}
@@ -361,13 +361,17 @@ def micro_benchmarks(args, g, lib, zk, w_dev, torch):
     return res
 
 
-def cpu_baseline(args, g):
-    """The oracle's C++ restatement of the reference CPU prover timed on this box's host cores, on a bounded
-    sample (one proof at 2^sample_log_n constraints), scaled linearly to 2^log_n."""
+def cpu_baseline(args, g, zk_full=None, wit_full=None):
+    """The oracle's C++ restatement of the reference CPU prover timed on this box's host cores: one proof of
+    the benchmark's own 2^log_n fixture when --cpu-sample-log-n equals log_n (default), else a smaller
+    instance of the same circuit family scaled linearly."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_cpu as oc
-    sl = args.sample_log_n
-    zk, wit, _ = make_fixture(g, sl)
+    sl = min(args.cpu_sample_log_n, args.log_n)
+    if sl == args.log_n and zk_full is not None:
+        zk, wit = zk_full, wit_full
+    else:
+        zk, wit, _ = make_fixture(g, sl)
     cores = oc.ncpu()
     t0 = time.perf_counter()
     _, _, _, phases = oc.prove(zk, wit, MASK_R, MASK_S, nthreads=cores)
@@ -376,8 +380,9 @@ def cpu_baseline(args, g):
     labels = ["building 'ABC'", "computing the quotient (FFTs)", "computing pi_A (G1 MSM)", "computing rho (G1 MSM)",
               "computing pi_B (G2 MSM)", "computing pi_C (2x G1 MSM)"]
     return {"value": 1.0 / (dt * scale), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "one full CPU proof at 2^%d constraints (%.2f s), scaled x%d to 2^%d; C++ restatement of the "
-                      "reference decomposition (constantine unavailable)" % (sl, dt, int(scale), args.log_n),
+            "sample": "one full CPU proof at 2^%d constraints (%.2f s)%s; C++ restatement of the reference "
+                      "decomposition (constantine unavailable)" %
+                      (sl, dt, "" if scale == 1 else ", scaled x%d to 2^%d" % (int(scale), args.log_n)),
             "phase_seconds_sample": {k: round(v, 4) for k, v in zip(labels, phases)}}
 
 
@@ -388,7 +393,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=20, help="log2 of the constraint count (headline: 20)")
-    ap.add_argument("--sample-log-n", type=int, default=16, help="CPU-baseline sample size (log2 constraints)")
+    ap.add_argument("--sample-log-n", type=int, default=18,
+                    help="--impl reference: constraints (log2) of the bounded CPU sample proved per step")
+    ap.add_argument("--cpu-sample-log-n", type=int, default=20,
+                    help="cpu_baseline of the main arm: constraints (log2) of the one CPU proof that is timed")
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
