@@ -31,6 +31,8 @@ struct MsmGeometry {
   uint32_t max_items = 0;  // upper bound on work items
 };
 
+constexpr uint32_t MSM_FIXUP_SMALL_MAX = 16;   // buckets with at most this many items are merged by one thread
+
 int msm_pick_window(size_t n, bool precomp);
 MsmGeometry msm_geometry(size_t n, int c, bool precomp);
 
@@ -49,8 +51,8 @@ class MsmSorter {
   const uint32_t* item_start() const { return item_start_.as<uint32_t>(); }
   const uint32_t* item_bucket() const { return item_bucket_.as<uint32_t>(); }
   const uint32_t* items_sorted() const { return item_idx_[1].as<uint32_t>(); }
-  const uint32_t* multi_list() const { return multi_.as<uint32_t>() + 1; }
-  const uint32_t* multi_count() const { return multi_.as<uint32_t>(); }
+  // buckets split into several items: [count_small, count_big, small[nbuckets], big[nbuckets]]
+  const uint32_t* multi() const { return multi_.as<uint32_t>(); }
 
  private:
   MsmGeometry g_;

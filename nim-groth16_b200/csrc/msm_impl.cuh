@@ -89,17 +89,35 @@ __global__ void __launch_bounds__(128) k_bucket_accumulate(AccSets<F> sets, cons
   else st_vec(sets.partials[set] + id, acc);
 }
 
-// buckets split into several work items: sum their partials (rare; skewed scalar distributions)
+// buckets split into 2..MSM_FIXUP_SMALL_MAX work items (e.g. the heavier low buckets fed by the short top
+// window): one thread adds the few partial sums.  grid.x covers nbuckets threads, grid.y = point sets.
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_fixup_small(AccSets<F> sets, const uint32_t* __restrict__ item_start,
+                                                            const uint32_t* __restrict__ multi) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= multi[0]) return;
+  const int set = blockIdx.y;
+  const uint32_t b = multi[2 + i];
+  const uint32_t i0 = item_start[b], i1 = item_start[b + 1];
+  XYZZ<F> acc = ld_vec(sets.partials[set] + i0);
+  for (uint32_t k = i0 + 1; k < i1; k++) {
+    XYZZ<F> o = ld_vec(sets.partials[set] + k);
+    xyzz_add_ni(acc, acc, o);
+  }
+  st_vec(sets.buckets[set] + b, acc);
+}
+
+// giant buckets (skewed scalar distributions, degenerate top window): a block tree-sums the partials
 template <class F>
 __global__ void __launch_bounds__(128) k_bucket_fixup(AccSets<F> sets, const uint32_t* __restrict__ item_start,
-                                                      const uint32_t* __restrict__ multi_count,
-                                                      const uint32_t* __restrict__ multi_list) {
+                                                      const uint32_t* __restrict__ multi, uint32_t nbuckets) {
   extern __shared__ uint4 red_raw[];
   XYZZ<F>* red = reinterpret_cast<XYZZ<F>*>(red_raw);
   const int set = blockIdx.y;
-  const uint32_t count = *multi_count;
+  const uint32_t count = multi[1];
+  const uint32_t* list = multi + 2 + nbuckets;
   for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
-    uint32_t b = multi_list[i];
+    uint32_t b = list[i];
     uint32_t i0 = item_start[b], i1 = item_start[b + 1];
     XYZZ<F> acc = xyzz_inf<F>();
     for (uint32_t k = i0 + threadIdx.x; k < i1; k += blockDim.x) {
@@ -170,7 +188,7 @@ __global__ void __launch_bounds__(128) k_reduce_level(ReduceLevel<F> a) {
   if (threadIdx.x == 0) st_vec(a.out_r[set] + (size_t)w * gridDim.x + blockIdx.x, sum);
 }
 
-constexpr int MSM_MAX_LEVELS = 8;
+constexpr int MSM_MAX_LEVELS = 12;
 template <class F>
 struct ReduceFinal {
   const XYZZ<F>* r[MsmAccumulator<F>::MAX_SETS][MSM_MAX_LEVELS];   // block sums of each level
@@ -338,7 +356,10 @@ void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, i
   lvl_n[0] = g.nb;
   while (lvl_n[nlevels] > 1) {
     G16_REQUIRE(nlevels < MSM_MAX_LEVELS, "too many reduction levels");
-    uint32_t L = lvl_n[nlevels] >= 16u ? 16u : lvl_n[nlevels];
+    // level 1 is throughput-bound (fan-in 16 keeps its work at 2.1 additions per bucket); the upper levels are
+    // latency-bound chains of tiny launches, so they use fan-in 4 (7 sequential additions per level)
+    uint32_t want = nlevels == 0 ? 16u : 4u;
+    uint32_t L = lvl_n[nlevels] >= want ? want : lvl_n[nlevels];
     uint32_t threads = lvl_n[nlevels] / L;
     lvl_L[nlevels] = L;
     lvl_tpb[nlevels] = threads < 128u ? (threads < 32u ? 32u : threads) : 128u;
@@ -381,9 +402,12 @@ void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, i
                                                    g.max_items, g.T);
   G16_LAUNCH_CHECK();
   if (profile) G16_CUDA(cudaEventRecord(pev_[1], stream));
+  dim3 sgrid(div_up(g.nbuckets, 128), (unsigned)nsets);
+  k_bucket_fixup_small<F><<<sgrid, 128, 0, stream>>>(sets, sorter.item_start(), sorter.multi());
+  G16_LAUNCH_CHECK();
   dim3 fgrid(148, (unsigned)nsets);
-  k_bucket_fixup<F><<<fgrid, 128, 128 * sizeof(XYZZ<F>), stream>>>(sets, sorter.item_start(), sorter.multi_count(),
-                                                                   sorter.multi_list());
+  k_bucket_fixup<F><<<fgrid, 128, 128 * sizeof(XYZZ<F>), stream>>>(sets, sorter.item_start(), sorter.multi(),
+                                                                   g.nbuckets);
   G16_LAUNCH_CHECK();
   // bucket reduction: one launch per level, then the per-set Horner over the levels
   ReduceFinal<F> fin;

@@ -47,13 +47,16 @@ MsmGeometry msm_geometry(size_t n, int c, bool precomp) {
   g.nbuckets = precomp ? g.nb : (uint32_t)g.nwin * g.nb;
   g.m = (size_t)g.nwin * n;
   G16_REQUIRE(g.m < ((size_t)1 << 31), "MSM pair count must fit 31 bits");
-  // a work item is at most T additions.  Items are sorted by length, so T only has to bound the tail of a
-  // launch, not balance lanes; it is kept well above the heaviest regular bucket (the top window of a 254-bit
-  // scalar has few significant bits, which makes the low buckets several times heavier than the average) and
-  // only splits the giant buckets of skewed scalar distributions (many 0/1/small witness values).
+  // A work item is at most T additions.  Items are sorted by length so lanes are balanced for any T; T bounds
+  // the serial latency of one thread (~11 us per G1 addition with the SM fully occupied): a launch processes
+  // m additions on ~75k resident threads, so an item longer than about m / 150k additions would outlive the
+  // rest of the kernel.  It must stay above twice the mean bucket length so that regular buckets are not
+  // split.  Heavier buckets -- the top window of a 254-bit scalar has few significant bits and concentrates
+  // its n digits on 2^(254 mod c) buckets, and real witnesses are full of 0/1/small values -- become several
+  // items whose partial sums are merged by k_bucket_fixup_small / k_bucket_fixup.
   size_t avg = g.m / g.nbuckets + 1;
-  size_t T = 16 * avg;
-  if (T < 256) T = 256;
+  size_t T = g.m / 150000;
+  if (T < 2 * avg + 16) T = 2 * avg + 16;
   if (T > 32768) T = 32768;
   g.T = (uint32_t)T;
   g.max_items = g.nbuckets + (uint32_t)(g.m / T) + 1;
@@ -117,7 +120,10 @@ __global__ void k_bucket_chunks(const uint32_t* __restrict__ start, uint32_t nbu
 __global__ void k_items_init(uint32_t* __restrict__ key, uint32_t* __restrict__ idx, uint32_t max_items, uint32_t T,
                              uint32_t* __restrict__ multi_count) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t == 0) *multi_count = 0;
+  if (t == 0) {
+    multi_count[0] = 0;
+    multi_count[1] = 0;
+  }
   if (t >= max_items) return;
   key[t] = T;        // padding sorts after every real item (real keys are T - len <= T - 1)
   idx[t] = t;
@@ -137,9 +143,14 @@ __global__ void k_make_items(const uint32_t* __restrict__ start, const uint32_t*
     item_bucket[i0 + k] = b;
     item_key[i0 + k] = T - l;
   }
-  if (i1 - i0 > 1) {
-    uint32_t slot = atomicAdd(multi, 1u);
-    multi[1 + slot] = b;
+  if (i1 - i0 > 1) {           // layout of `multi`: [count_small, count_big, small[nbuckets], big[nbuckets]]
+    if (i1 - i0 <= MSM_FIXUP_SMALL_MAX) {
+      uint32_t slot = atomicAdd(multi, 1u);
+      multi[2 + slot] = b;
+    } else {
+      uint32_t slot = atomicAdd(multi + 1, 1u);
+      multi[2 + nbuckets + slot] = b;
+    }
   }
 }
 
@@ -175,7 +186,7 @@ void MsmSorter::run(const Fr* scalars, bool scalars_mont, const MsmGeometry& g, 
     item_key_[i].ensure((size_t)g.max_items * 4);
     item_idx_[i].ensure((size_t)g.max_items * 4);
   }
-  multi_.ensure(((size_t)g.nbuckets + 2) * 4);
+  multi_.ensure((2 * (size_t)g.nbuckets + 4) * 4);
 
   k_msm_digits<<<div_up(g.n, 256), 256, 0, stream>>>(scalars, (uint32_t)g.n, scalars_mont ? 1 : 0, g.c, g.nwin, g.nb,
                                                      g.precomp ? 1 : 0, g.nbuckets, keys_[0].as<uint32_t>(),

@@ -256,9 +256,17 @@ Prover::Prover(const g16_zkey_view& zk, int shard_index, int shard_count)
   flavour_ = zk.flavour;
   n_ = (size_t)1 << log_n_;
   for (int i = 0; i < 24; i++) ev_[i] = nullptr;
-  G16_CUDA(cudaStreamCreateWithFlags(&main_, cudaStreamNonBlocking));
-  for (int i = 0; i < 3; i++) G16_CUDA(cudaStreamCreateWithFlags(&st_[i], cudaStreamNonBlocking));
-  G16_CUDA(cudaStreamCreateWithFlags(&st_mask_, cudaStreamNonBlocking));
+  // Priorities order the kernels that compete for the SMs: the witness sort and the G2 MSM (longest
+  // latency-bound reduction tail) first, then the fused G1 witness MSMs (their result feeds the early
+  // assembly), the H chain last -- so the single-warp tails of one MSM overlap with the accumulation of another.
+  int prio_lo = 0, prio_hi = 0;
+  G16_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));      // hi is numerically smaller
+  int p_mid = prio_hi + (prio_lo - prio_hi) / 2;
+  G16_CUDA(cudaStreamCreateWithPriority(&main_, cudaStreamNonBlocking, prio_hi));
+  G16_CUDA(cudaStreamCreateWithPriority(&st_[0], cudaStreamNonBlocking, prio_lo));    // ABC, quotient, H1
+  G16_CUDA(cudaStreamCreateWithPriority(&st_[1], cudaStreamNonBlocking, p_mid));      // witness sort, A1+B1+C1
+  G16_CUDA(cudaStreamCreateWithPriority(&st_[2], cudaStreamNonBlocking, prio_hi));    // B2
+  G16_CUDA(cudaStreamCreateWithPriority(&st_mask_, cudaStreamNonBlocking, prio_hi));
   for (int i = 0; i < 24; i++) G16_CUDA(cudaEventCreate(&ev_[i]));
 
   // this context's contiguous ranges (msm.nim:107-111): witness-indexed arrays and the H array
