@@ -470,19 +470,35 @@ G16_HD Fp2 fneg(const Fp2& a) {
   return r;
 }
 G16_HD Fp2 fdbl(const Fp2& a) { return fadd(a, a); }
+// Out-of-line Fp multiply for the Fp2 layer: a G2 mixed addition contains 28 Fp multiplications; inlining
+// them all makes a ~100 KB loop body that misses the instruction cache (ncu: no_instruction stalls), so the
+// Fp2 operations call one shared copy instead (by-value arguments travel in registers).
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+static inline
+#endif
+Fp fmul_call(Fp a, Fp b) { return fmul(a, b); }
+
+#ifndef G16_FP2_INLINE_MUL
+#define G16_FP2_MUL(a, b) fmul_call(a, b)
+#else
+#define G16_FP2_MUL(a, b) fmul(a, b)
+#endif
+
 G16_HD Fp2 fmul(const Fp2& a, const Fp2& b) {  // Karatsuba, 3 Fp mul
-  Fp t0 = fmul(a.c0, b.c0);
-  Fp t1 = fmul(a.c1, b.c1);
-  Fp s = fmul(fadd(a.c0, a.c1), fadd(b.c0, b.c1));
+  Fp t0 = G16_FP2_MUL(a.c0, b.c0);
+  Fp t1 = G16_FP2_MUL(a.c1, b.c1);
+  Fp s = G16_FP2_MUL(fadd(a.c0, a.c1), fadd(b.c0, b.c1));
   Fp2 r;
   r.c0 = fsub(t0, t1);
   r.c1 = fsub(fsub(s, t0), t1);
   return r;
 }
 G16_HD Fp2 fsqr(const Fp2& a) {  // 2 Fp mul
-  Fp t = fmul(a.c0, a.c1);
+  Fp t = G16_FP2_MUL(a.c0, a.c1);
   Fp2 r;
-  r.c0 = fmul(fadd(a.c0, a.c1), fsub(a.c0, a.c1));
+  r.c0 = G16_FP2_MUL(fadd(a.c0, a.c1), fsub(a.c0, a.c1));
   r.c1 = fdbl(t);
   return r;
 }

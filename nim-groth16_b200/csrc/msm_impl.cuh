@@ -13,7 +13,12 @@
 //   k_build_table        precomputed layout: 2^(c w) P_i for every window, batch-normalised to affine
 #pragma once
 #include "msm.cuh"
+#include <stdlib.h>
 #include "msm_digits.cuh"
+
+#ifndef G16_G2_MINB_DEFAULT
+#define G16_G2_MINB_DEFAULT 2
+#endif
 
 namespace g16 {
 
@@ -59,8 +64,8 @@ struct AccSets {
 // ---------------------------------------------------------------------------------------
 // bucket accumulation
 // ---------------------------------------------------------------------------------------
-template <class F>
-__global__ void __launch_bounds__(128) k_bucket_accumulate(AccSets<F> sets, const uint32_t* __restrict__ vals,
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_bucket_accumulate(AccSets<F> sets, const uint32_t* __restrict__ vals,
                                                            const uint32_t* __restrict__ start,
                                                            const uint32_t* __restrict__ item_start,
                                                            const uint32_t* __restrict__ item_bucket,
@@ -344,6 +349,30 @@ float MsmAccumulator<F>::last_accum_ms() const {
   return ms;
 }
 
+// occupancy variant of the accumulate kernel: G1 fits 4 CTAs/SM by itself; for G2 the register budget is a
+// trade-off between spills and resident warps (G16_G2_MINB overrides the default for experiments)
+template <class F>
+static void launch_accumulate(dim3 grid, cudaStream_t stream, const AccSets<F>& sets, const MsmSorter& sorter,
+                              const MsmGeometry& g) {
+  static int minb = -1;
+  if (minb < 0) {
+    const char* e = getenv("G16_G2_MINB");
+    minb = e ? atoi(e) : G16_G2_MINB_DEFAULT;
+  }
+#define G16_ACC_ARGS sets, sorter.vals(), sorter.start(), sorter.item_start(), sorter.item_bucket(), \
+                     sorter.items_sorted(), g.nbuckets, g.max_items, g.T
+  if (sizeof(F) == sizeof(Fp)) {
+    k_bucket_accumulate<F, 1><<<grid, 128, 0, stream>>>(G16_ACC_ARGS);
+  } else if (minb == 3) {
+    k_bucket_accumulate<F, 3><<<grid, 128, 0, stream>>>(G16_ACC_ARGS);
+  } else if (minb == 4) {
+    k_bucket_accumulate<F, 4><<<grid, 128, 0, stream>>>(G16_ACC_ARGS);
+  } else {
+    k_bucket_accumulate<F, 2><<<grid, 128, 0, stream>>>(G16_ACC_ARGS);
+  }
+#undef G16_ACC_ARGS
+}
+
 template <class F>
 void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, int nsets, cudaStream_t stream) {
   G16_REQUIRE(nsets >= 1 && nsets <= MAX_SETS, "MsmAccumulator: 1..3 point sets");
@@ -397,9 +426,7 @@ void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, i
     G16_CUDA(cudaEventRecord(pev_[0], stream));
   }
   dim3 agrid(div_up(g.max_items, 128), (unsigned)nsets);
-  k_bucket_accumulate<F><<<agrid, 128, 0, stream>>>(sets, sorter.vals(), sorter.start(), sorter.item_start(),
-                                                   sorter.item_bucket(), sorter.items_sorted(), g.nbuckets,
-                                                   g.max_items, g.T);
+  launch_accumulate<F>(agrid, stream, sets, sorter, g);
   G16_LAUNCH_CHECK();
   if (profile) G16_CUDA(cudaEventRecord(pev_[1], stream));
   dim3 sgrid(div_up(g.nbuckets, 128), (unsigned)nsets);
