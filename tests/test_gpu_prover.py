@@ -256,3 +256,27 @@ def test_context_creation_is_stream_ordered_under_dirty_memory(g):
         ctx.close()
         assert np.array_equal(got.pi_b, want.pi_b) and np.array_equal(got.pi_a, want.pi_a)
         assert np.array_equal(got.pi_c, want.pi_c)
+
+
+@pytest.mark.parametrize("flav", [1, 0])
+def test_gpu_proofs_pass_the_pairing_verifier(g, flav):
+    """north_star: "proofs that pass verifier.nim" -- generateProof (random masks, prover.nim:312-319) on the GPU,
+    verifyProof (verifier.nim:31-52) restated with real pairings in the oracle."""
+    import bn254_pairing as bp
+    e = E()
+    r1cs, wit = g.synthetic_chain_circuit(50, seed=9)
+    zk = g.create_fake_circuit_setup(r1cs, flav)                 # random toxic waste (fake_setup.nim:330)
+    ctx = g.ProverContext(zk)
+    prf = g.generate_proof(4, False, zk, g.Witness(values=wit), ctx=ctx)
+    prf0 = g.generate_proof_with_trivial_mask(4, False, zk, g.Witness(values=wit), ctx=ctx)
+    ctx.close()
+    assert not np.array_equal(prf.pi_a, prf0.pi_a)               # the masks do randomise the proof
+    args = (e.g1_from_array(zk.alpha1)[0], e.g2_from_array(zk.beta2)[0], e.g2_from_array(zk.gamma2)[0],
+            e.g2_from_array(zk.delta2)[0], e.g1_from_array(zk.pointsIC), e.fr_from_std(prf.publicIO))
+    for p in (prf, prf0):
+        assert bp.verify_proof(*args, e.g1_from_array(p.pi_a)[0], e.g2_from_array(p.pi_b)[0],
+                               e.g1_from_array(p.pi_c)[0])
+    # snarkjs-format export of the same proof (export_json.nim:25-80)
+    txt = g.export_json.proof_json(prf)
+    assert '"protocol": "groth16"' in txt and str(e.g1_from_array(prf.pi_a)[0][0]) in txt
+    assert g.export_json.public_io_json(prf).count('"') == 2 * zk.npubs
