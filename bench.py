@@ -189,35 +189,60 @@ def run_ours(args):
     h2d_bytes = nvars * 32
     d2h_bytes = 256
 
+    # `depth` proofs in flight (default 2): consecutive proofs overlap, so the latency-bound tail of one
+    # (bucket-reduction levels, assembly, the all-gather) hides behind the accumulation kernels of the next.
+    # Each proof in flight owns a context (its own copy of the resident tables).  depth 1 = strictly
+    # sequential proofs, reported as `sequential`.
+    depth = max(1, args.pipeline)
     if world == 1:
-        ctx = g.ProverContext(zk)
+        ctxs = [g.ProverContext(zk) for _ in range(depth)]
+        ctx = ctxs[0]
 
-        def step_resident():
-            return ctx.prove_dev(w_dev.data_ptr(), mask)[0]
-
-        def step_e2e():
-            return ctx.prove_ptr(w_pinned.data_ptr(), mask, E.FORM_STD)[0]
+        def make_runner(ptr, mem_kind):
+            def run(steps):
+                last = None
+                for i in range(steps):
+                    c = ctxs[i % depth]
+                    if i >= depth:
+                        last = c.wait()[0]
+                    c.submit(ptr, mask, E.FORM_STD, mem_kind)
+                for i in range(min(depth, steps)):
+                    last = ctxs[(steps - min(depth, steps) + i) % depth].wait()[0]
+                return last
+            return run
     else:
-        sp = g.parallel.ShardedProver(zk, rank, world, device=local)
-        ctx = sp.ctx
+        sps = [g.parallel.ShardedProver(zk, rank, world, device=local) for _ in range(depth)]
+        ctxs = [sp.ctx for sp in sps]
+        ctx = ctxs[0]
 
-        def step_resident():
-            return sp.prove_raw(w_dev.data_ptr(), MEM_DEVICE, mask)
+        def make_runner(ptr, mem_kind):
+            def run(steps):
+                last = None
+                for i in range(steps):
+                    sp = sps[i % depth]
+                    sp.partials_submit(ptr, mem_kind)
+                    if i >= depth - 1 and depth > 1:
+                        last = sps[(i - (depth - 1)) % depth].complete(mask)
+                    elif depth == 1:
+                        last = sp.complete(mask)
+                for j in range(max(0, steps - (depth - 1)), steps):
+                    if depth > 1:
+                        last = sps[j % depth].complete(mask)
+                return last
+            return run
 
-        def step_e2e():
-            return sp.prove_raw(w_pinned.data_ptr(), MEM_HOST, mask)
+    run_resident = make_runner(w_dev.data_ptr(), MEM_DEVICE)
+    run_e2e = make_runner(w_pinned.data_ptr(), MEM_HOST)
 
-    def timed(step, steps, warmup):
-        for _ in range(warmup):
-            step()
+    def timed(run, steps, warmup):
+        run(warmup)
         barrier()
         ms = C.c_float()
         l0 = lib.g16_kernel_launch_count()
         _lib.check(lib.g16_ctx_timer_start(ctx._h))
         t0 = time.perf_counter()
-        raw = None
-        for _ in range(steps):
-            raw = step()
+        raw = run(steps)
+        torch.cuda.synchronize()
         _lib.check(lib.g16_ctx_timer_stop(ctx._h, C.byref(ms)))
         wall = (time.perf_counter() - t0) * 1e3
         launches = lib.g16_kernel_launch_count() - l0
@@ -232,11 +257,19 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    dev_ms, wall_ms, launches, raw = timed(step_resident, args.steps, args.warmup)
+    dev_ms, wall_ms, launches, raw = timed(run_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_dev_ms, e2e_wall_ms, _, raw2 = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    e2e_dev_ms, e2e_wall_ms, _, raw2 = timed(run_e2e, args.steps, max(depth, args.warmup // 2))
+    seq = None
+    if depth > 1:                      # strictly sequential proofs on one context, for the latency figure
+        save = depth
+        depth = 1
+        seq_dev_ms, seq_wall_ms, _, raw3 = timed(make_runner(w_dev.data_ptr(), MEM_DEVICE), args.steps, 2)
+        depth = save
+        assert bytes(raw3.pi_c) == bytes(raw.pi_c)
+        seq = {"ms_per_proof": seq_dev_ms / args.steps, "proofs_per_s": args.steps / (seq_dev_ms * 1e-3)}
     assert bytes(raw.pi_c) == bytes(raw2.pi_c) and bytes(raw.pi_a) == bytes(raw2.pi_a)
-    stats = ctx.last_stats
+    stats = ctx.last_stats or {}
 
     out = None
     if rank == 0:
@@ -244,12 +277,13 @@ def run_ours(args):
         out = {"metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "u32x8-montgomery", "data": "synthetic",
-               "config": workload_config(args, world),
-               "wall_ms_per_step": wall_ms / args.steps,
+               "config": dict(workload_config(args, world), proofs_in_flight=depth),
+               "wall_ms_per_step": wall_ms / args.steps, "sequential": seq,
                "e2e": {"value": args.steps / (e2e_wall_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                        "d2h_bytes_per_step": d2h_bytes, "device_ms_per_step": e2e_dev_ms / args.steps,
                        "wall_ms_per_step": e2e_wall_ms / args.steps,
-                       "api": "g16_prove (host witness)" if world == 1 else "g16_prove_partials + all-gather + g16_prove_finish"},
+                       "api": "g16_prove_submit/wait (host witness)" if world == 1 else
+                              "g16_prove_partials_submit/wait + all-gather + g16_prove_finish_submit/wait"},
                "gpu_launches": int(launches), "clocks": clocks,
                "phase_ms_last_step": {k: round(v, 3) for k, v in stats.items() if k.startswith("ms_")}}
 
@@ -262,7 +296,8 @@ def run_ours(args):
         except Exception as ex:      # the checker being unavailable must not kill the GPU number
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
                                    "sample": "failed: %r" % (ex,)}
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -402,6 +437,7 @@ def main():
                     help="--impl reference: constraints (log2) of the bounded CPU sample proved per step")
     ap.add_argument("--cpu-sample-log-n", type=int, default=20,
                     help="cpu_baseline of the main arm: constraints (log2) of the one CPU proof that is timed")
+    ap.add_argument("--pipeline", type=int, default=2, help="proofs in flight (1 = strictly sequential proofs)")
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

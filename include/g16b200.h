@@ -150,6 +150,15 @@ void g16_ctx_destroy(g16_ctx* ctx);
 int g16_prove(g16_ctx* ctx, const uint64_t* witness, int witness_form, const uint64_t r_std[4],
               const uint64_t s_std[4], g16_proof* proof, g16_stats* stats);
 
+/* Asynchronous form of g16_prove: submit enqueues the whole proof on the context's streams and returns;
+ * wait blocks until the proof is in host memory.  One proof in flight per context; several contexts (of the
+ * same or of different zkeys) may be in flight at once, which overlaps the latency-bound tail of one proof
+ * (bucket-reduction levels, assembly) with the accumulation kernels of the next.  The witness buffer must
+ * stay valid until g16_prove_wait returns. */
+int g16_prove_submit(g16_ctx* ctx, const void* witness, int witness_form, int witness_mem_kind,
+                     const uint64_t r_std[4], const uint64_t s_std[4]);
+int g16_prove_wait(g16_ctx* ctx, g16_proof* proof, g16_stats* stats);
+
 /* Same with the witness already resident in device memory (standard form). */
 int g16_prove_dev(g16_ctx* ctx, const void* witness_std_dev, const uint64_t r_std[4], const uint64_t s_std[4],
                   g16_proof* proof, g16_stats* stats);
@@ -160,6 +169,12 @@ int g16_prove_dev(g16_ctx* ctx, const void* witness_std_dev, const uint64_t r_st
  *   any rank:    g16_prove_finish over the gathered records -> the proof. */
 int g16_prove_partials(g16_ctx* ctx, const uint64_t* witness, int witness_form, int witness_mem_kind,
                        void* partials_dev, g16_stats* stats);
+/* asynchronous forms (see g16_prove_submit) */
+int g16_prove_partials_submit(g16_ctx* ctx, const void* witness, int witness_form, int witness_mem_kind,
+                              void* partials_dev);
+int g16_prove_partials_wait(g16_ctx* ctx, g16_stats* stats);
+int g16_prove_finish_submit(g16_ctx* ctx, const void* gathered_partials_dev, int count, const uint64_t r_std[4],
+                            const uint64_t s_std[4]);     /* completed by g16_prove_wait */
 /* the five MSM sums of the most recent g16_prove* call on this context, as affine records (diagnostics) */
 int g16_ctx_last_partials(g16_ctx* ctx, void* partials_dev);
 int g16_prove_finish(g16_ctx* ctx, const void* gathered_partials_dev, int count, const uint64_t r_std[4],

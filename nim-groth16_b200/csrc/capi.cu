@@ -130,6 +130,7 @@ using namespace g16;
 
 struct g16_ctx {
   std::unique_ptr<Prover> prover;
+  uint64_t launches0 = 0, launches1 = 0;
 };
 
 struct g16_msm_plan {
@@ -244,28 +245,46 @@ int g16_ctx_create(const g16_zkey_view* zkey, int shard_index, int shard_count, 
 }
 void g16_ctx_destroy(g16_ctx* ctx) { delete ctx; }
 
-static void prove_common(g16_ctx* ctx, const void* witness, int form, int mem_kind, const uint64_t r[4],
-                         const uint64_t s[4], g16_proof* proof, g16_stats* stats) {
+static void prove_submit(g16_ctx* ctx, const void* witness, int form, int mem_kind, const uint64_t r[4],
+                         const uint64_t s[4]) {
   G16_REQUIRE(ctx && ctx->prover, "context is null");
   G16_REQUIRE(ctx->prover->shard_count() == 1, "g16_prove needs an unsharded context; use g16_prove_partials");
-  G16_REQUIRE(proof != nullptr, "proof output is null");
-  uint64_t l0 = g_launches.load();
-  if (stats) memset(stats, 0, sizeof(*stats));
+  G16_REQUIRE(!ctx->prover->in_flight(), "a proof is already in flight on this context");
+  ctx->launches0 = g_launches.load();
   Prover& p = *ctx->prover;
   p.start_mask(r, s);
   p.load_witness(witness, form, mem_kind);
-  p.run_msms(stats);
-  p.finish(proof, stats);
-  if (stats) stats->kernel_launches = (uint32_t)(g_launches.load() - l0);
+  p.run_msms(nullptr);
+  p.finish_async();
+  ctx->launches1 = g_launches.load();
+}
+static void prove_wait(g16_ctx* ctx, g16_proof* proof, g16_stats* stats) {
+  G16_REQUIRE(ctx && ctx->prover, "context is null");
+  if (stats) memset(stats, 0, sizeof(*stats));
+  ctx->prover->wait(proof, stats);
+  if (stats) stats->kernel_launches = (uint32_t)(ctx->launches1 - ctx->launches0);
 }
 
 int g16_prove(g16_ctx* ctx, const uint64_t* witness, int witness_form, const uint64_t r_std[4],
               const uint64_t s_std[4], g16_proof* proof, g16_stats* stats) {
-  return guard([&] { prove_common(ctx, witness, witness_form, G16_MEM_HOST, r_std, s_std, proof, stats); });
+  return guard([&] {
+    prove_submit(ctx, witness, witness_form, G16_MEM_HOST, r_std, s_std);
+    prove_wait(ctx, proof, stats);
+  });
 }
 int g16_prove_dev(g16_ctx* ctx, const void* witness_std_dev, const uint64_t r_std[4], const uint64_t s_std[4],
                   g16_proof* proof, g16_stats* stats) {
-  return guard([&] { prove_common(ctx, witness_std_dev, G16_FORM_STD, G16_MEM_DEVICE, r_std, s_std, proof, stats); });
+  return guard([&] {
+    prove_submit(ctx, witness_std_dev, G16_FORM_STD, G16_MEM_DEVICE, r_std, s_std);
+    prove_wait(ctx, proof, stats);
+  });
+}
+int g16_prove_submit(g16_ctx* ctx, const void* witness, int witness_form, int witness_mem_kind,
+                     const uint64_t r_std[4], const uint64_t s_std[4]) {
+  return guard([&] { prove_submit(ctx, witness, witness_form, witness_mem_kind, r_std, s_std); });
+}
+int g16_prove_wait(g16_ctx* ctx, g16_proof* proof, g16_stats* stats) {
+  return guard([&] { prove_wait(ctx, proof, stats); });
 }
 
 int g16_prove_partials(g16_ctx* ctx, const uint64_t* witness, int witness_form, int witness_mem_kind,
@@ -277,9 +296,28 @@ int g16_prove_partials(g16_ctx* ctx, const uint64_t* witness, int witness_form, 
     if (stats) memset(stats, 0, sizeof(*stats));
     Prover& p = *ctx->prover;
     p.load_witness(witness, witness_form, witness_mem_kind);
-    p.run_msms(stats);
-    p.partials_to_affine(partials_dev);
+    p.run_msms(nullptr);
+    p.partials_to_affine_async(partials_dev);
+    p.partials_wait(stats);
     if (stats) stats->kernel_launches = (uint32_t)(g_launches.load() - l0);
+  });
+}
+int g16_prove_partials_submit(g16_ctx* ctx, const void* witness, int witness_form, int witness_mem_kind,
+                              void* partials_dev) {
+  return guard([&] {
+    G16_REQUIRE(ctx && ctx->prover, "context is null");
+    G16_REQUIRE(partials_dev != nullptr, "partials buffer is null");
+    Prover& p = *ctx->prover;
+    p.load_witness(witness, witness_form, witness_mem_kind);
+    p.run_msms(nullptr);
+    p.partials_to_affine_async(partials_dev);
+  });
+}
+int g16_prove_partials_wait(g16_ctx* ctx, g16_stats* stats) {
+  return guard([&] {
+    G16_REQUIRE(ctx && ctx->prover, "context is null");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    ctx->prover->partials_wait(stats);
   });
 }
 
@@ -299,6 +337,17 @@ int g16_prove_finish(g16_ctx* ctx, const void* gathered_partials_dev, int count,
     p.start_mask(r_std, s_std);
     p.sum_partials(gathered_partials_dev, count);
     p.finish(proof, nullptr);
+  });
+}
+int g16_prove_finish_submit(g16_ctx* ctx, const void* gathered_partials_dev, int count, const uint64_t r_std[4],
+                            const uint64_t s_std[4]) {
+  return guard([&] {
+    G16_REQUIRE(ctx && ctx->prover, "context is null");
+    G16_REQUIRE(gathered_partials_dev != nullptr, "partials buffer is null");
+    Prover& p = *ctx->prover;
+    p.start_mask(r_std, s_std);
+    p.sum_partials(gathered_partials_dev, count);
+    p.finish_async();
   });
 }
 

@@ -448,22 +448,33 @@ void Prover::run_msms(g16_stats* stats) {
     G16_CUDA(cudaStreamWaitEvent(main_, ev_[13 + i], 0));
   }
   G16_CUDA(cudaEventRecord(ev_[18], main_));
-  if (stats) {
-    G16_CUDA(cudaStreamSynchronize(main_));
-    cudaEventElapsedTime(&stats->ms_abc, ev_[1], ev_[2]);
-    cudaEventElapsedTime(&stats->ms_quotient, ev_[2], ev_[3]);
-    cudaEventElapsedTime(&stats->ms_msm_h, ev_[3], ev_[4]);
-    cudaEventElapsedTime(&stats->ms_sort_witness, ev_[5], ev_[6]);
-    cudaEventElapsedTime(&stats->ms_msm_g1_witness, ev_[6], ev_[7]);
-    cudaEventElapsedTime(&stats->ms_msm_b2, ev_[8], ev_[9]);
-    cudaEventElapsedTime(&stats->ms_h2d, ev_[20], ev_[21]);
-  }
+  (void)stats;   // phase times are read by collect_stats() once the work has completed
 }
 
-void Prover::partials_to_affine(void* partials_dev) {
+// valid after the main stream has been synchronised past the events of the last run_msms()
+void Prover::collect_stats(g16_stats* stats) {
+  if (!stats) return;
+  cudaEventElapsedTime(&stats->ms_abc, ev_[1], ev_[2]);
+  cudaEventElapsedTime(&stats->ms_quotient, ev_[2], ev_[3]);
+  cudaEventElapsedTime(&stats->ms_msm_h, ev_[3], ev_[4]);
+  cudaEventElapsedTime(&stats->ms_sort_witness, ev_[5], ev_[6]);
+  cudaEventElapsedTime(&stats->ms_msm_g1_witness, ev_[6], ev_[7]);
+  cudaEventElapsedTime(&stats->ms_msm_b2, ev_[8], ev_[9]);
+  cudaEventElapsedTime(&stats->ms_h2d, ev_[20], ev_[21]);
+}
+
+void Prover::partials_to_affine_async(void* partials_dev) {
   k_partials_to_affine<<<1, 160, 0, main_>>>(results_.as<MsmResults>(), reinterpret_cast<PartialsAffine*>(partials_dev));
   G16_LAUNCH_CHECK();
-  G16_CUDA(cudaStreamSynchronize(main_));
+  G16_CUDA(cudaEventRecord(ev_[10], main_));
+}
+void Prover::partials_wait(g16_stats* stats) {
+  G16_CUDA(cudaEventSynchronize(ev_[10]));
+  collect_stats(stats);
+}
+void Prover::partials_to_affine(void* partials_dev) {
+  partials_to_affine_async(partials_dev);
+  partials_wait(nullptr);
 }
 
 void Prover::sum_partials(const void* gathered_dev, int count) {
@@ -490,8 +501,8 @@ void Prover::start_mask(const uint64_t r[4], const uint64_t s[4]) {
   early_done_ = false;
 }
 
-void Prover::finish(g16_proof* proof, g16_stats* stats) {
-  G16_REQUIRE(proof != nullptr, "proof output is null");
+// enqueue the rest of the proof (assembly + 256-byte copy to pinned memory); returns without waiting
+void Prover::finish_async() {
   G16_REQUIRE(mask_started_, "finish without start_mask");
   MaskTerms* m = mask_.as<MaskTerms>();
   G16_CUDA(cudaEventRecord(ev_[19], main_));
@@ -506,12 +517,26 @@ void Prover::finish(g16_proof* proof, g16_stats* stats) {
   early_done_ = false;
   G16_CUDA(cudaMemcpyAsync(proof_pinned_, proof_.p, sizeof(g16_proof), cudaMemcpyDeviceToHost, main_));
   G16_CUDA(cudaEventRecord(ev_[22], main_));
-  G16_CUDA(cudaStreamSynchronize(main_));
+  in_flight_ = true;
+}
+
+// wait for the proof enqueued by finish_async()
+void Prover::wait(g16_proof* proof, g16_stats* stats) {
+  G16_REQUIRE(proof != nullptr, "proof output is null");
+  G16_REQUIRE(in_flight_, "no proof in flight on this context");
+  G16_CUDA(cudaEventSynchronize(ev_[22]));
+  in_flight_ = false;
   memcpy(proof, proof_pinned_, sizeof(g16_proof));
   if (stats) {
+    collect_stats(stats);
     cudaEventElapsedTime(&stats->ms_assemble, ev_[19], ev_[22]);
     cudaEventElapsedTime(&stats->ms_total, ev_[20], ev_[22]);
   }
+}
+
+void Prover::finish(g16_proof* proof, g16_stats* stats) {
+  finish_async();
+  wait(proof, stats);
 }
 
 }  // namespace g16

@@ -39,8 +39,14 @@ class Prover {
   ~Prover();
   // witness upload (host or device source) into the resident standard-form buffer
   void load_witness(const void* w, int form, int mem_kind);
-  void run_msms(g16_stats* stats);                     // ABC, quotient, five MSMs -> results_
-  void partials_to_affine(void* partials_dev);         // results_ -> g16_partials (device)
+  void run_msms(g16_stats* stats);                     // ABC, quotient, five MSMs -> results_ (asynchronous)
+  void collect_stats(g16_stats* stats);                // phase times of the last run (after completion)
+  void partials_to_affine(void* partials_dev);         // results_ -> g16_partials (device), synchronous
+  void partials_to_affine_async(void* partials_dev);
+  void partials_wait(g16_stats* stats);
+  void finish_async();                                 // enqueue assembly + copy-out
+  void wait(g16_proof* proof, g16_stats* stats);       // completion of finish_async()
+  bool in_flight() const { return in_flight_; }
   void sum_partials(const void* gathered_dev, int count);   // gathered g16_partials -> results_
   void start_mask(const uint64_t r[4], const uint64_t s[4]);   // mask terms on their own stream
   void finish(g16_proof* proof, g16_stats* stats);             // assemble (waits for start_mask)
@@ -66,7 +72,7 @@ class Prover {
   SparseCsr csr_;
   DevBuf dtab1_, dtab2_;   // 2^j * delta1 / delta2
   DevBuf spec_, witness_, staging_, abc_, qs_, results_, mask_, proof_, early_;
-  bool mask_started_ = false, early_done_ = false;
+  bool mask_started_ = false, early_done_ = false, in_flight_ = false;
   cudaStream_t main_ = nullptr, st_mask_ = nullptr, st_[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_[24];
   cudaEvent_t tev_[2] = {nullptr, nullptr};

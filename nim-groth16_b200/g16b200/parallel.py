@@ -51,6 +51,29 @@ class ShardedProver:
             allp = self.partials.view(1, -1)
         return self.ctx.prove_finish(allp.data_ptr(), self.world, mask)
 
+    # asynchronous halves, for overlapping consecutive proofs (one ShardedProver per proof in flight)
+    def partials_submit(self, witness_ptr: int, mem_kind: int):
+        _lib.check(_lib.load().g16_prove_partials_submit(self.ctx._h, witness_ptr, FORM_STD, mem_kind,
+                                                         self.partials.data_ptr()))
+
+    def complete(self, mask: Mask, group=None):
+        """Waits for this rank's partial sums, all-gathers them, assembles; returns the raw proof."""
+        import ctypes as C
+        import torch
+        lib = _lib.load()
+        _lib.check(lib.g16_prove_partials_wait(self.ctx._h, None))
+        if self.world > 1:
+            allp = gather_partials(self.partials, group)
+            torch.cuda.current_stream().synchronize()
+        else:
+            allp = self.partials.view(1, -1)
+        from .prover import _limbs4
+        _lib.check(lib.g16_prove_finish_submit(self.ctx._h, allp.data_ptr(), self.world, _limbs4(mask.r),
+                                               _limbs4(mask.s)))
+        raw = _lib.ProofRaw()
+        _lib.check(lib.g16_prove_wait(self.ctx._h, C.byref(raw), None))
+        return raw
+
     def prove(self, witness: np.ndarray, mask: Mask, group=None) -> Proof:
         w = np.ascontiguousarray(witness, dtype=np.uint64).reshape(-1, 4)
         raw = self.prove_raw(w.ctypes.data, MEM_HOST, mask, group)

@@ -145,6 +145,18 @@ class ProverContext:
         self.last_stats = st.as_dict()
         return raw, self.last_stats
 
+    def submit(self, witness_ptr: int, mask: Mask, witness_form: int = FORM_STD, mem_kind: int = MEM_HOST):
+        """g16_prove_submit: enqueue a proof and return; the witness buffer must outlive wait()."""
+        _lib.check(_lib.load().g16_prove_submit(self._h, witness_ptr, witness_form, mem_kind, _limbs4(mask.r),
+                                                _limbs4(mask.s)))
+
+    def wait(self):
+        """g16_prove_wait -> (ProofRaw, stats)."""
+        raw, st = _lib.ProofRaw(), _lib.Stats()
+        _lib.check(_lib.load().g16_prove_wait(self._h, C.byref(raw), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return raw, self.last_stats
+
     def prove_partials(self, witness_ptr: int, witness_form: int, mem_kind: int, partials_dev_ptr: int):
         st = _lib.Stats()
         _lib.check(_lib.load().g16_prove_partials(self._h, witness_ptr, witness_form, mem_kind, partials_dev_ptr,
