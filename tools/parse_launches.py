@@ -21,7 +21,7 @@ def seg_report(title, seg):
         print("  %8.3f ms %5.1f%% x%-3d %s" % (t, 100 * t / tot, c, k))
 i0 = idx[-1]
 j = i0
-while 'k_assemble' not in rows[j][1]: j += 1
+while 'k_assemble_final' not in rows[j][1]: j += 1
 # include the mask-term kernel launched just before the witness copy
 k0 = i0
 while k0 > 0 and 'k_mask_terms' not in rows[k0][1]: k0 -= 1
