@@ -11,6 +11,14 @@ n = 1 << log_n
 dl = E.random_fr_std(n, seed=5)
 pts = g.fixed_base_g2(dl) if g2 else g.fixed_base_g1(dl)
 sc = E.random_fr_std(n, seed=4)
+if os.environ.get("PROBE_SKEWED"):       # 40 % zeros, 20 % ones, 20 % below 2^16, 20 % uniform
+    rng = np.random.Generator(np.random.PCG64(8))
+    cls = rng.integers(0, 5, size=n)
+    sc[cls <= 1] = 0
+    sc[cls == 2] = np.array([1, 0, 0, 0], np.uint64)
+    small = cls == 3
+    sc[small, 1:] = 0
+    sc[small, 0] &= np.uint64(0xFFFF)
 d_pts = torch.from_numpy(pts.view(np.int64).copy()).to("cuda")
 d_sc = torch.from_numpy(sc.view(np.int64).copy()).to("cuda")
 res = torch.zeros(64, dtype=torch.int64, device="cuda")
