@@ -378,6 +378,57 @@ G16_HD Fe<P> fmul(const Fe<P>& a, const Fe<P>& b) {
 #endif
 }
 
+// Two independent Montgomery products with their carry chains interleaved row by row: the rows of one
+// product do not depend on the rows of the other, so a warp exposes two independent IMAD.WIDE chains to the
+// scheduler (used by the Fp2 layer, whose kernels run at only two warps per scheduler).
+template <class P>
+G16_HD void fmul2(const Fe<P>& a, const Fe<P>& b, const Fe<P>& c, const Fe<P>& d, Fe<P>& r1, Fe<P>& r2) {
+#if defined(__CUDA_ARCH__)
+  uint32_t t[2][8], u[2][8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) t[0][k] = t[1][k] = u[0][k] = u[1][k] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t* X = t[i & 1];
+    uint32_t* Y = t[(i + 1) & 1];
+    uint32_t* X2 = u[i & 1];
+    uint32_t* Y2 = u[(i + 1) & 1];
+    const uint32_t bi = b.v[i], di = d.v[i];
+    mad_row_shift(X, Y[0], a.v[1], a.v[3], a.v[5], a.v[7], bi);
+    mad_row_shift(X2, Y2[0], c.v[1], c.v[3], c.v[5], c.v[7], di);
+    mad_row_carry(Y, X[7], a.v[0], a.v[2], a.v[4], a.v[6], bi);
+    mad_row_carry(Y2, X2[7], c.v[0], c.v[2], c.v[4], c.v[6], di);
+    const uint32_t m = Y[0] * P::INV;
+    const uint32_t m2 = Y2[0] * P::INV;
+    mad_row_nc(X, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+    mad_row_nc(X2, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m2);
+    mad_row_carry(Y, X[7], P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);
+    mad_row_carry(Y2, X2[7], P::mod(0), P::mod(2), P::mod(4), P::mod(6), m2);
+  }
+  merge8_ip(t[1], t[0]);
+  merge8_ip(u[1], u[0]);
+  uint32_t pm[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) pm[k] = P::mod(k);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    r1.v[k] = t[1][k];
+    r2.v[k] = u[1][k];
+  }
+  Fe<P> v1 = r1, v2 = r2;
+  uint32_t bw1 = sub8_ip(v1.v, pm);
+  uint32_t bw2 = sub8_ip(v2.v, pm);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    r1.v[k] = bw1 ? r1.v[k] : v1.v[k];
+    r2.v[k] = bw2 ? r2.v[k] : v2.v[k];
+  }
+#else
+  r1 = fmul(a, b);
+  r2 = fmul(c, d);
+#endif
+}
+
 template <class P>
 G16_HD Fe<P> fsqr(const Fe<P>& a) {
   return fmul(a, a);
@@ -480,25 +531,51 @@ static inline
 #endif
 Fp fmul_call(Fp a, Fp b) { return fmul(a, b); }
 
+struct FpPair {
+  Fp a, b;
+};
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+static inline
+#endif
+FpPair fmul2_call(Fp a, Fp b, Fp c, Fp d) {
+  FpPair r;
+  fmul2(a, b, c, d, r.a, r.b);
+  return r;
+}
+
 #ifndef G16_FP2_INLINE_MUL
 #define G16_FP2_MUL(a, b) fmul_call(a, b)
 #else
 #define G16_FP2_MUL(a, b) fmul(a, b)
 #endif
 
-G16_HD Fp2 fmul(const Fp2& a, const Fp2& b) {  // Karatsuba, 3 Fp mul
+G16_HD Fp2 fmul(const Fp2& a, const Fp2& b) {  // Karatsuba, 3 Fp mul (two of them interleaved)
+#ifdef G16_FP2_NO_PAIRING
   Fp t0 = G16_FP2_MUL(a.c0, b.c0);
   Fp t1 = G16_FP2_MUL(a.c1, b.c1);
+#else
+  FpPair pr = fmul2_call(a.c0, b.c0, a.c1, b.c1);
+  Fp t0 = pr.a, t1 = pr.b;
+#endif
   Fp s = G16_FP2_MUL(fadd(a.c0, a.c1), fadd(b.c0, b.c1));
   Fp2 r;
   r.c0 = fsub(t0, t1);
   r.c1 = fsub(fsub(s, t0), t1);
   return r;
 }
-G16_HD Fp2 fsqr(const Fp2& a) {  // 2 Fp mul
+G16_HD Fp2 fsqr(const Fp2& a) {  // 2 Fp mul, interleaved
+#ifdef G16_FP2_NO_PAIRING
   Fp t = G16_FP2_MUL(a.c0, a.c1);
   Fp2 r;
   r.c0 = G16_FP2_MUL(fadd(a.c0, a.c1), fsub(a.c0, a.c1));
+#else
+  FpPair pr = fmul2_call(a.c0, a.c1, fadd(a.c0, a.c1), fsub(a.c0, a.c1));
+  Fp t = pr.a;
+  Fp2 r;
+  r.c0 = pr.b;
+#endif
   r.c1 = fdbl(t);
   return r;
 }
