@@ -191,12 +191,12 @@ def run_ours(args):
 
     # `depth` proofs in flight (default 2): consecutive proofs overlap, so the latency-bound tail of one
     # (bucket-reduction levels, assembly, the all-gather) hides behind the accumulation kernels of the next.
-    # Each proof in flight owns a context (its own copy of the resident tables).  depth 1 = strictly
-    # sequential proofs, reported as `sequential`.
+    # Each proof in flight owns a context slot; the slots share one resident key (g16_ctx_clone).  depth 1 =
+    # strictly sequential proofs, reported as `sequential`.
     depth = max(1, args.pipeline)
     if world == 1:
-        ctxs = [g.ProverContext(zk) for _ in range(depth)]
-        ctx = ctxs[0]
+        ctx = g.ProverContext(zk)
+        ctxs = [ctx] + [ctx.clone() for _ in range(depth - 1)]
 
         def make_runner(ptr, mem_kind):
             def run(steps):
@@ -211,7 +211,8 @@ def run_ours(args):
                 return last
             return run
     else:
-        sps = [g.parallel.ShardedProver(zk, rank, world, device=local) for _ in range(depth)]
+        sp0 = g.parallel.ShardedProver(zk, rank, world, device=local)
+        sps = [sp0] + [g.parallel.ShardedProver(zk, rank, world, device=local, share=sp0) for _ in range(depth - 1)]
         ctxs = [sp.ctx for sp in sps]
         ctx = ctxs[0]
 

@@ -143,6 +143,10 @@ typedef struct g16_ctx g16_ctx;
  * select the contiguous point range [N*k/G, N*(k+1)/G) of every MSM, the chunking of msm.nim:107-115;
  * pass 0, 1 for the whole key on one GPU. */
 int g16_ctx_create(const g16_zkey_view* zkey, int shard_index, int shard_count, g16_ctx** out);
+/* Another proof slot over the SAME resident key (tables, CSR rows, spec points are shared and read-only; only
+ * the per-proof scratch and streams are new): use it with g16_prove_submit to keep several proofs in flight.
+ * The key's device memory is released when the last context referring to it is destroyed. */
+int g16_ctx_clone(g16_ctx* ctx, g16_ctx** out);
 void g16_ctx_destroy(g16_ctx* ctx);
 
 /* generateProofWithMask (prover.nim:215-304).  witness: nvars elements of `witness_form` (host);

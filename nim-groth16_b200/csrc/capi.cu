@@ -243,6 +243,14 @@ int g16_ctx_create(const g16_zkey_view* zkey, int shard_index, int shard_count, 
     *out = c.release();
   });
 }
+int g16_ctx_clone(g16_ctx* ctx, g16_ctx** out) {
+  return guard([&] {
+    G16_REQUIRE(ctx && ctx->prover && out, "null argument");
+    std::unique_ptr<g16_ctx> c(new g16_ctx());
+    c->prover.reset(new Prover(ctx->prover->resident()));
+    *out = c.release();
+  });
+}
 void g16_ctx_destroy(g16_ctx* ctx) { delete ctx; }
 
 static void prove_submit(g16_ctx* ctx, const void* witness, int form, int mem_kind, const uint64_t r[4],

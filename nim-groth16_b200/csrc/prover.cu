@@ -244,17 +244,80 @@ static void make_table(DevBuf& table, const void* src, size_t lo, size_t hi, siz
   G16_CUDA(cudaStreamSynchronize(stream));   // raw is released on return
 }
 
-Prover::Prover(const g16_zkey_view& zk, int shard_index, int shard_count)
-    : shard_index_(shard_index), shard_count_(shard_count) {
+Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_in)
+    : shard_index(shard_index_in), shard_count(shard_count_in) {
   G16_REQUIRE(shard_count >= 1 && shard_index >= 0 && shard_index < shard_count, "bad shard index/count");
   G16_REQUIRE(zk.log_domain >= 1 && zk.log_domain <= 26, "domain size must be 2^1 .. 2^26 (prover.nim:101)");
   G16_REQUIRE(zk.flavour == G16_FLAVOUR_JENSGROTH || zk.flavour == G16_FLAVOUR_SNARKJS, "unknown flavour");
   G16_REQUIRE(zk.nvars >= zk.npubs + 1, "nvars must be at least npubs + 1");
-  nvars_ = zk.nvars;
-  npubs_ = zk.npubs;
-  log_n_ = zk.log_domain;
-  flavour_ = zk.flavour;
-  n_ = (size_t)1 << log_n_;
+  nvars = zk.nvars;
+  npubs = zk.npubs;
+  log_n = zk.log_domain;
+  flavour = zk.flavour;
+  n = (size_t)1 << log_n;
+  cudaStream_t main_ = nullptr;
+  G16_CUDA(cudaStreamCreateWithFlags(&main_, cudaStreamNonBlocking));
+  // this context's contiguous ranges (msm.nim:107-111): witness-indexed arrays and the H array
+  shard_range(nvars, shard_index, shard_count, v_lo, v_hi);
+  shard_range(n, shard_index, shard_count, h_lo, h_hi);
+  const size_t nv = v_hi - v_lo, nh = h_hi - h_lo;
+  if (nv) gw = msm_geometry(nv, msm_pick_window(nv, true), true);
+  if (nh) gh = msm_geometry(nh, msm_pick_window(nh, true), true);
+  make_table<Fp>(tabA1, zk.points_a1, v_lo, v_hi, 0, gw.c ? gw.c : 4, zk.mem_kind, main_);
+  make_table<Fp>(tabB1, zk.points_b1, v_lo, v_hi, 0, gw.c ? gw.c : 4, zk.mem_kind, main_);
+  make_table<Fp2>(tabB2, zk.points_b2, v_lo, v_hi, 0, gw.c ? gw.c : 4, zk.mem_kind, main_);
+  {
+    // C1[j - npubs - 1] multiplies witness[j] (prover.nim:262-264): pad so that table index == witness index
+    size_t first = (size_t)npubs + 1;
+    size_t from = v_lo > first ? v_lo : first;            // first witness index of this shard with a C point
+    size_t pad = v_hi > from ? from - v_lo : nv;
+    size_t c_lo = from - first, c_hi = v_hi > from ? v_hi - first : c_lo;
+    make_table<Fp>(tabC1, zk.points_c1, c_lo, c_hi, pad, gw.c ? gw.c : 4, zk.mem_kind, main_);
+  }
+  make_table<Fp>(tabH1, zk.points_h1, h_lo, h_hi, 0, gh.c ? gh.c : 4, zk.mem_kind, main_);
+
+  // coefficient list -> CSR rows (once per zkey)
+  {
+    size_t rec = zk.coeff_format == G16_COEFF_PACKED44_R2 ? 44 : 48;
+    DevBuf raw;
+    raw.ensure(zk.ncoeffs * rec + 16);
+    if (zk.ncoeffs) {
+      G16_REQUIRE(zk.coeffs != nullptr, "zkey view: missing coefficient list");
+      G16_CUDA(cudaMemcpyAsync(raw.p, zk.coeffs, zk.ncoeffs * rec,
+                               zk.mem_kind == G16_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                               main_));
+    }
+    coeffs_to_csr(csr, raw.p, zk.ncoeffs, (int)zk.coeff_format, (int)log_n, nvars, main_);
+  }
+
+  SpecPointsDev sp;
+  memcpy(&sp.alpha1, zk.alpha1, 64);
+  memcpy(&sp.beta1, zk.beta1, 64);
+  memcpy(&sp.delta1, zk.delta1, 64);
+  memcpy(&sp.beta2, zk.beta2, 128);
+  memcpy(&sp.delta2, zk.delta2, 128);
+  spec.ensure(sizeof(SpecPointsDev));
+  G16_CUDA(cudaMemcpyAsync(spec.p, &sp, sizeof(sp), cudaMemcpyHostToDevice, main_));
+  G16_CUDA(cudaFuncSetAttribute(k_mask_terms, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(256 * sizeof(G2XYZZ))));
+  dtab1.ensure(256 * sizeof(G1XYZZ));
+  dtab2.ensure(256 * sizeof(G2XYZZ));
+  k_delta_tables<<<1, 64, 0, main_>>>(spec.as<SpecPointsDev>(), dtab1.as<G1XYZZ>(), dtab2.as<G2XYZZ>());
+  G16_LAUNCH_CHECK();
+  G16_CUDA(cudaStreamSynchronize(main_));
+
+  ntt_prepare((int)log_n, main_);
+  G16_CUDA(cudaStreamSynchronize(main_));
+  cudaStreamDestroy(main_);
+}
+
+
+size_t Resident::bytes() const {
+  return tabA1.bytes + tabB1.bytes + tabC1.bytes + tabH1.bytes + tabB2.bytes + csr.ptr.bytes + csr.other.bytes +
+         csr.vals.bytes + dtab1.bytes + dtab2.bytes;
+}
+
+void Prover::init_slot() {
   for (int i = 0; i < 24; i++) ev_[i] = nullptr;
   // Priorities order the kernels that compete for the SMs: the witness sort and the G2 MSM (longest
   // latency-bound reduction tail) first, then the fused G1 witness MSMs (their result feeds the early
@@ -269,71 +332,26 @@ Prover::Prover(const g16_zkey_view& zk, int shard_index, int shard_count)
   G16_CUDA(cudaStreamCreateWithPriority(&st_mask_, cudaStreamNonBlocking, prio_hi));
   for (int i = 0; i < 24; i++) G16_CUDA(cudaEventCreate(&ev_[i]));
 
-  // this context's contiguous ranges (msm.nim:107-111): witness-indexed arrays and the H array
-  shard_range(nvars_, shard_index, shard_count, v_lo_, v_hi_);
-  shard_range(n_, shard_index, shard_count, h_lo_, h_hi_);
-  const size_t nv = v_hi_ - v_lo_, nh = h_hi_ - h_lo_;
-  if (nv) gw_ = msm_geometry(nv, msm_pick_window(nv, true), true);
-  if (nh) gh_ = msm_geometry(nh, msm_pick_window(nh, true), true);
-  make_table<Fp>(tabA1_, zk.points_a1, v_lo_, v_hi_, 0, gw_.c ? gw_.c : 4, zk.mem_kind, main_);
-  make_table<Fp>(tabB1_, zk.points_b1, v_lo_, v_hi_, 0, gw_.c ? gw_.c : 4, zk.mem_kind, main_);
-  make_table<Fp2>(tabB2_, zk.points_b2, v_lo_, v_hi_, 0, gw_.c ? gw_.c : 4, zk.mem_kind, main_);
-  {
-    // C1[j - npubs - 1] multiplies witness[j] (prover.nim:262-264): pad so that table index == witness index
-    size_t first = (size_t)npubs_ + 1;
-    size_t from = v_lo_ > first ? v_lo_ : first;            // first witness index of this shard with a C point
-    size_t pad = v_hi_ > from ? from - v_lo_ : nv;
-    size_t c_lo = from - first, c_hi = v_hi_ > from ? v_hi_ - first : c_lo;
-    make_table<Fp>(tabC1_, zk.points_c1, c_lo, c_hi, pad, gw_.c ? gw_.c : 4, zk.mem_kind, main_);
-  }
-  make_table<Fp>(tabH1_, zk.points_h1, h_lo_, h_hi_, 0, gh_.c ? gh_.c : 4, zk.mem_kind, main_);
-
-  // coefficient list -> CSR rows (once per zkey)
-  {
-    size_t rec = zk.coeff_format == G16_COEFF_PACKED44_R2 ? 44 : 48;
-    DevBuf raw;
-    raw.ensure(zk.ncoeffs * rec + 16);
-    if (zk.ncoeffs) {
-      G16_REQUIRE(zk.coeffs != nullptr, "zkey view: missing coefficient list");
-      G16_CUDA(cudaMemcpyAsync(raw.p, zk.coeffs, zk.ncoeffs * rec,
-                               zk.mem_kind == G16_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                               main_));
-    }
-    coeffs_to_csr(csr_, raw.p, zk.ncoeffs, (int)zk.coeff_format, (int)log_n_, nvars_, main_);
-  }
-
-  SpecPointsDev sp;
-  memcpy(&sp.alpha1, zk.alpha1, 64);
-  memcpy(&sp.beta1, zk.beta1, 64);
-  memcpy(&sp.delta1, zk.delta1, 64);
-  memcpy(&sp.beta2, zk.beta2, 128);
-  memcpy(&sp.delta2, zk.delta2, 128);
-  spec_.ensure(sizeof(SpecPointsDev));
-  G16_CUDA(cudaMemcpyAsync(spec_.p, &sp, sizeof(sp), cudaMemcpyHostToDevice, main_));
-  G16_CUDA(cudaFuncSetAttribute(k_mask_terms, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(256 * sizeof(G2XYZZ))));
-  dtab1_.ensure(256 * sizeof(G1XYZZ));
-  dtab2_.ensure(256 * sizeof(G2XYZZ));
-  k_delta_tables<<<1, 64, 0, main_>>>(spec_.as<SpecPointsDev>(), dtab1_.as<G1XYZZ>(), dtab2_.as<G2XYZZ>());
-  G16_LAUNCH_CHECK();
-  G16_CUDA(cudaStreamSynchronize(main_));
-
-  witness_.ensure((size_t)nvars_ * sizeof(Fr));
-  abc_.ensure(3 * n_ * sizeof(Fr));
-  qs_.ensure(n_ * sizeof(Fr));
+  witness_.ensure((size_t)R->nvars * sizeof(Fr));
+  abc_.ensure(3 * R->n * sizeof(Fr));
+  qs_.ensure(R->n * sizeof(Fr));
   results_.ensure(sizeof(MsmResults));
   G16_CUDA(cudaMemset(results_.p, 0, sizeof(MsmResults)));   // all-zero XYZZ == infinity (empty shards)
   mask_.ensure(sizeof(MaskTerms));
   proof_.ensure(sizeof(g16_proof));
   early_.ensure(sizeof(G1XYZZ));
   G16_CUDA(cudaMallocHost(reinterpret_cast<void**>(&proof_pinned_), sizeof(g16_proof)));
-  ntt_prepare((int)log_n_, main_);
-  G16_CUDA(cudaStreamSynchronize(main_));
 }
 
+Prover::Prover(const g16_zkey_view& zk, int shard_index, int shard_count)
+    : R(std::make_shared<Resident>(zk, shard_index, shard_count)) {
+  init_slot();
+}
+
+Prover::Prover(std::shared_ptr<Resident> resident) : R(std::move(resident)) { init_slot(); }
+
 size_t Prover::resident_bytes() const {
-  return tabA1_.bytes + tabB1_.bytes + tabC1_.bytes + tabH1_.bytes + tabB2_.bytes + csr_.ptr.bytes + csr_.other.bytes +
-         csr_.vals.bytes + witness_.bytes + abc_.bytes + qs_.bytes + sortW_.workspace_bytes() +
+  return R->bytes() + witness_.bytes + abc_.bytes + qs_.bytes + sortW_.workspace_bytes() +
          sortH_.workspace_bytes() + accW_.workspace_bytes() + accH_.workspace_bytes() + accB2_.workspace_bytes();
 }
 
@@ -369,7 +387,7 @@ float Prover::timer_stop() {
 void Prover::load_witness(const void* w, int form, int mem_kind) {
   G16_REQUIRE(w != nullptr, "witness is null");
   G16_REQUIRE(form == G16_FORM_MONT || form == G16_FORM_STD, "unknown witness form");
-  size_t bytes = (size_t)nvars_ * sizeof(Fr);
+  size_t bytes = (size_t)R->nvars * sizeof(Fr);
   cudaMemcpyKind kind = mem_kind == G16_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   G16_CUDA(cudaEventRecord(ev_[20], main_));
   if (form == G16_FORM_STD) {
@@ -377,7 +395,7 @@ void Prover::load_witness(const void* w, int form, int mem_kind) {
   } else {
     staging_.ensure(bytes);
     G16_CUDA(cudaMemcpyAsync(staging_.p, w, bytes, kind, main_));
-    fr_from_mont(staging_.as<Fr>(), witness_.as<Fr>(), nvars_, main_);
+    fr_from_mont(staging_.as<Fr>(), witness_.as<Fr>(), R->nvars, main_);
   }
   G16_CUDA(cudaEventRecord(ev_[21], main_));
 }
@@ -390,18 +408,18 @@ void Prover::run_msms(g16_stats* stats) {
   for (int i = 0; i < 3; i++) G16_CUDA(cudaStreamWaitEvent(st_[i], ev_[0], 0));
   MsmResults* res = results_.as<MsmResults>();
   const Fr* w = witness_.as<Fr>();
-  const size_t nv = v_hi_ - v_lo_, nh = h_hi_ - h_lo_;
+  const size_t nv = R->v_hi - R->v_lo, nh = R->h_hi - R->h_lo;
 
   // stream 0: ABC -> quotient -> sort of qs -> MSM over the H table   (prover.nim:245-260, 301)
   G16_CUDA(cudaEventRecord(ev_[1], st_[0]));
-  build_abc(csr_, w, abc_.as<Fr>(), (int)log_n_, st_[0]);
+  build_abc(R->csr, w, abc_.as<Fr>(), (int)R->log_n, st_[0]);
   G16_CUDA(cudaEventRecord(ev_[2], st_[0]));
-  quotient(abc_.as<Fr>(), qs_.as<Fr>(), (int)log_n_, (int)flavour_, st_[0]);
+  quotient(abc_.as<Fr>(), qs_.as<Fr>(), (int)R->log_n, (int)R->flavour, st_[0]);
   G16_CUDA(cudaEventRecord(ev_[3], st_[0]));
   if (nh) {
-    sortH_.run(qs_.as<Fr>() + h_lo_, true, gh_, st_[0]);
+    sortH_.run(qs_.as<Fr>() + R->h_lo, true, R->gh, st_[0]);
     MsmPointSet<Fp> hs;
-    hs.points = tabH1_.as<G1Affine>();
+    hs.points = R->tabH1.as<G1Affine>();
     hs.result = &res->h1;
     accH_.run(sortH_, &hs, 1, st_[0]);
   }
@@ -410,21 +428,21 @@ void Prover::run_msms(g16_stats* stats) {
   // stream 1: one digit/sort pass over the witness, then A1, B1, C1 in the same launches
   // (prover.nim:282, 288, 302; zs = witness[npubs+1 ..] through the padded C1 table)
   G16_CUDA(cudaEventRecord(ev_[5], st_[1]));
-  if (nv) sortW_.run(w + v_lo_, false, gw_, st_[1]);
+  if (nv) sortW_.run(w + R->v_lo, false, R->gw, st_[1]);
   G16_CUDA(cudaEventRecord(ev_[6], st_[1]));
   G16_CUDA(cudaStreamWaitEvent(st_[2], ev_[6], 0));
   if (nv) {
     MsmPointSet<Fp> ws[3];
-    ws[0].points = tabA1_.as<G1Affine>();
+    ws[0].points = R->tabA1.as<G1Affine>();
     ws[0].result = &res->a1;
-    ws[1].points = tabB1_.as<G1Affine>();
+    ws[1].points = R->tabB1.as<G1Affine>();
     ws[1].result = &res->b1;
-    ws[2].points = tabC1_.as<G1Affine>();
+    ws[2].points = R->tabC1.as<G1Affine>();
     ws[2].result = &res->c1;
     accW_.run(sortW_, ws, 3, st_[1]);
   }
   G16_CUDA(cudaEventRecord(ev_[7], st_[1]));
-  if (mask_started_ && shard_count_ == 1) {
+  if (mask_started_ && R->shard_count == 1) {
     // the MSM-dependent scalar multiplications start now and overlap with the B2 / H work still in flight
     G16_CUDA(cudaStreamWaitEvent(st_[1], ev_[23], 0));
     k_assemble_early<<<1, 64, 0, st_[1]>>>(results_.as<MsmResults>(), mask_.as<MaskTerms>(), proof_.as<g16_proof>(),
@@ -437,7 +455,7 @@ void Prover::run_msms(g16_stats* stats) {
   G16_CUDA(cudaEventRecord(ev_[8], st_[2]));
   if (nv) {
     MsmPointSet<Fp2> bs;
-    bs.points = tabB2_.as<G2Affine>();
+    bs.points = R->tabB2.as<G2Affine>();
     bs.result = &res->b2;
     accB2_.run(sortW_, &bs, 1, st_[2]);
   }
@@ -493,8 +511,8 @@ void Prover::start_mask(const uint64_t r[4], const uint64_t s[4]) {
   memcpy(rs + 8, s, 32);
   G16_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(m) + offsetof(MaskTerms, r), rs, 64, cudaMemcpyHostToDevice,
                            st_mask_));
-  k_mask_terms<<<4, 256, 256 * sizeof(G2XYZZ), st_mask_>>>(spec_.as<SpecPointsDev>(), dtab1_.as<G1XYZZ>(),
-                                                           dtab2_.as<G2XYZZ>(), m);
+  k_mask_terms<<<4, 256, 256 * sizeof(G2XYZZ), st_mask_>>>(R->spec.as<SpecPointsDev>(), R->dtab1.as<G1XYZZ>(),
+                                                           R->dtab2.as<G2XYZZ>(), m);
   G16_LAUNCH_CHECK();
   G16_CUDA(cudaEventRecord(ev_[23], st_mask_));
   mask_started_ = true;

@@ -1,6 +1,7 @@
 // Library-internal interface of prover.cu: the resident proving context.
 #pragma once
 #include <cuda_runtime.h>
+#include <memory>
 #include "../../include/g16b200.h"
 #include "abc.cuh"
 #include "common.cuh"
@@ -33,10 +34,29 @@ struct alignas(16) SpecPointsDev {    // SpecPoints (zkey_types.nim:24-31) neede
   G2Affine beta2, delta2;
 };
 
+// Everything that depends only on the zkey: built once, read-only afterwards, shared by all proofs in flight.
+struct Resident {
+  Resident(const g16_zkey_view& zk, int shard_index, int shard_count);
+  int shard_index, shard_count;
+  uint32_t nvars, npubs, log_n, flavour;
+  size_t n;
+  size_t v_lo, v_hi, h_lo, h_hi;       // this shard's ranges of the witness-indexed arrays and of H1 (msm.nim:107-111)
+  // window tables 2^(c w) P_i: A1, B1, C1 (padded to witness indices), H1 in G1; B2 in G2
+  DevBuf tabA1, tabB1, tabC1, tabH1, tabB2;
+  MsmGeometry gw, gh;
+  SparseCsr csr;
+  DevBuf spec;                         // SpecPointsDev
+  DevBuf dtab1, dtab2;                 // 2^j * delta1 / delta2
+  size_t bytes() const;
+};
+
+// One proof in flight: streams, scratch and the sorter / accumulator workspaces.
 class Prover {
  public:
   Prover(const g16_zkey_view& zk, int shard_index, int shard_count);
+  explicit Prover(std::shared_ptr<Resident> resident);   // another slot over the same resident key
   ~Prover();
+  std::shared_ptr<Resident> resident() const { return R; }
   // witness upload (host or device source) into the resident standard-form buffer
   void load_witness(const void* w, int form, int mem_kind);
   void run_msms(g16_stats* stats);                     // ABC, quotient, five MSMs -> results_ (asynchronous)
@@ -50,8 +70,8 @@ class Prover {
   void sum_partials(const void* gathered_dev, int count);   // gathered g16_partials -> results_
   void start_mask(const uint64_t r[4], const uint64_t s[4]);   // mask terms on their own stream
   void finish(g16_proof* proof, g16_stats* stats);             // assemble (waits for start_mask)
-  int shard_count() const { return shard_count_; }
-  uint32_t nvars() const { return nvars_; }
+  int shard_count() const { return R->shard_count; }
+  uint32_t nvars() const { return R->nvars; }
   Fr* witness_dev() { return witness_.as<Fr>(); }
   void sync();
   void timer_start();                 // CUDA event on the context's main stream
@@ -59,19 +79,12 @@ class Prover {
   size_t resident_bytes() const;
 
  private:
-  int shard_index_, shard_count_;
-  uint32_t nvars_, npubs_, log_n_, flavour_;
-  size_t n_;
-  size_t v_lo_, v_hi_, h_lo_, h_hi_;
-  // resident window tables (2^(c w) P_i): A1, B1, C1 (padded to witness indices), H1 in G1; B2 in G2
-  DevBuf tabA1_, tabB1_, tabC1_, tabH1_, tabB2_;
-  MsmGeometry gw_, gh_;
+  void init_slot();
+  std::shared_ptr<Resident> R;
   MsmSorter sortW_, sortH_;
   MsmAccumulator<Fp> accW_, accH_;
   MsmAccumulator<Fp2> accB2_;
-  SparseCsr csr_;
-  DevBuf dtab1_, dtab2_;   // 2^j * delta1 / delta2
-  DevBuf spec_, witness_, staging_, abc_, qs_, results_, mask_, proof_, early_;
+  DevBuf witness_, staging_, abc_, qs_, results_, mask_, proof_, early_;
   bool mask_started_ = false, early_done_ = false, in_flight_ = false;
   cudaStream_t main_ = nullptr, st_mask_ = nullptr, st_[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_[24];

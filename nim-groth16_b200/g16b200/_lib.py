@@ -70,6 +70,7 @@ SIGNATURES = {
     "g16_build_abc": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "g16_ctx_create": (C.c_int, [C.POINTER(ZkeyView), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "g16_ctx_clone": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "g16_ctx_destroy": (None, [C.c_void_p]),
     "g16_prove": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(ProofRaw),
                             C.POINTER(Stats)]),

@@ -33,12 +33,14 @@ def gather_partials(local: "torch.Tensor", group=None) -> "torch.Tensor":   # no
 class ShardedProver:
     """A prover context per rank; prove() returns the full proof on every rank."""
 
-    def __init__(self, zkey: ZKey, rank: int, world: int, device: Optional[int] = None):
+    def __init__(self, zkey: ZKey, rank: int, world: int, device: Optional[int] = None,
+                 share: Optional["ShardedProver"] = None):
         import torch
         self.rank, self.world = rank, world
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         _lib.check(_lib.load().g16_set_device(self.device.index))
-        self.ctx = ProverContext(zkey, rank, world)
+        # `share`: another slot over the same resident shard (g16_ctx_clone) for proofs in flight
+        self.ctx = share.ctx.clone() if share is not None else ProverContext(zkey, rank, world)
         self.partials = torch.zeros(_lib.PARTIALS_BYTES, dtype=torch.uint8, device=self.device)
 
     def prove_raw(self, witness_ptr: int, mem_kind: int, mask: Mask, group=None):

@@ -97,6 +97,15 @@ class ProverContext:
         self._keep = []          # uploaded; host copies no longer needed
         self.last_stats: Optional[dict] = None
 
+    def clone(self) -> "ProverContext":
+        """g16_ctx_clone: another proof slot sharing this context's resident key (for proofs in flight)."""
+        other = ProverContext.__new__(ProverContext)
+        other.zkey, other.shard_index, other.shard_count = self.zkey, self.shard_index, self.shard_count
+        other._keep, other.last_stats = [], None
+        other._h = C.c_void_p()
+        _lib.check(_lib.load().g16_ctx_clone(self._h, C.byref(other._h)))
+        return other
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             _lib.load().g16_ctx_destroy(self._h)

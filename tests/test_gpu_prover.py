@@ -293,7 +293,8 @@ def test_async_submit_wait_with_two_contexts_in_flight(g):
     ref = g.ProverContext(zk)
     want = [ref.prove(wit, m) for m in masks]
     ref.close()
-    ctxs = [g.ProverContext(zk), g.ProverContext(zk)]
+    first = g.ProverContext(zk)
+    ctxs = [first, first.clone()]                      # g16_ctx_clone: two slots, one resident key
     w_host = torch.from_numpy(np.ascontiguousarray(wit).view(np.int64).copy()).pin_memory()
     w_dev = w_host.to("cuda")
     got = [None] * 4
