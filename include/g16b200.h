@@ -261,7 +261,11 @@ int g16_fixed_base_g2(const uint64_t* scalars_std, size_t n, uint64_t* points_ou
 int g16_selftest(uint32_t seed, uint32_t cases);
 /* integer-pipe microbenchmark: sustained 32-bit multiply-add rate of all SMs.
  * kind 0 = mad.lo.u32, 1 = mad.hi.u32, 2 = lo/hi carry pairs (IMAD.WIDE.X), 3 = full Montgomery multiplies.
- * Reports operations (MAC32, or modmuls for kind 3) per second. */
+ * Reports operations (MAC32, or modmuls for kind 3) per second.
+ * FP64-pipe co-issue experiment: 4 = DFMA Montgomery multiplies (field_fp64.cuh) on the odd warps only,
+ * 5 = IMAD Montgomery multiplies on the even warps only, 6 = both at once (modmuls/s of the even warps; the odd
+ * warps do the same number of multiplies -- compare `ms` with kinds 4 and 5); 7 = DFMA multiplies on all warps;
+ * 8 / 9 = 2 of 8 / 6 of 8 warps on DFMA, the rest on IMAD (total modmuls/s). */
 int g16_bench_int_pipe(int kind, double* ops_per_sec, float* ms);
 /* number of kernels this library has launched in this process */
 uint64_t g16_kernel_launch_count(void);

@@ -3,6 +3,7 @@
 #include <vector>
 #include "common.cuh"
 #include "ec.cuh"
+#include "field_fp64.cuh"
 
 namespace g16 {
 
@@ -16,7 +17,7 @@ struct alignas(16) SelfCase {
 };
 struct alignas(16) SelfOut {
   Fr rmul, radd, rsub, rinv;
-  Fp pmul, psub;
+  Fp pmul, psub, pdmul;
   Fp2 qmul, qsqr;
   G1Affine g1;
   G2Affine g2;
@@ -29,6 +30,15 @@ static __host__ __device__ void self_eval(const SelfCase& c, SelfOut& o) {
   o.rinv = finv(c.ra);
   o.pmul = fmul(c.pa, c.pb);
   o.psub = fsub(c.pa, c.pb);
+#if defined(__CUDA_ARCH__)
+  o.pdmul = fd_to_fp(dfmul(fd_from_fp(c.pa), fd_from_fp(c.pb)));   // FP64-pipe multiplier: a*b*2^-260
+#else
+  {
+    Fp k = Fp::zero();
+    k.v[7] = 1u << 28;                                              // 2^252: fmul(x, k) = x * 2^-4
+    o.pdmul = fmul(fmul(c.pa, c.pb), k);
+  }
+#endif
   Fp2 x, y;
   x.c0 = c.pa;
   x.c1 = c.pb;
@@ -122,13 +132,13 @@ int selftest_run(uint32_t seed, uint32_t cases) {
     self_eval(in[i], want);
     if (memcmp(&want, &got[i], sizeof(SelfOut)) != 0) {
       if (!bad) {
-        const char* names[] = {"rmul", "radd", "rsub", "rinv", "pmul", "psub", "qmul", "qsqr", "g1", "g2"};
+        const char* names[] = {"rmul", "radd", "rsub", "rinv", "pmul", "psub", "pdmul", "qmul", "qsqr", "g1", "g2"};
         size_t offs[] = {offsetof(SelfOut, rmul), offsetof(SelfOut, radd), offsetof(SelfOut, rsub),
-                         offsetof(SelfOut, rinv), offsetof(SelfOut, pmul), offsetof(SelfOut, psub),
+                         offsetof(SelfOut, rinv), offsetof(SelfOut, pmul), offsetof(SelfOut, psub), offsetof(SelfOut, pdmul),
                          offsetof(SelfOut, qmul), offsetof(SelfOut, qsqr), offsetof(SelfOut, g1),
                          offsetof(SelfOut, g2), sizeof(SelfOut)};
         std::string msg = "selftest mismatch in case " + std::to_string(i) + ":";
-        for (int k = 0; k < 10; k++)
+        for (int k = 0; k < 11; k++)
           if (memcmp((char*)&want + offs[k], (char*)&got[i] + offs[k], offs[k + 1] - offs[k]) != 0)
             msg += std::string(" ") + names[k];
         set_last_error(msg);
@@ -217,6 +227,43 @@ __global__ void __launch_bounds__(256) k_ip_fmul(Fp* out, uint32_t a) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = fadd(x, z);
 }
 
+// FP64-pipe experiment: the DFMA Montgomery multiplier of field_fp64.cuh, same dependency pattern as k_ip_fmul
+// mode bit 0: even warps run the IMAD Montgomery multiply loop; bit 1: odd warps run the DFMA primitive loop
+__global__ void __launch_bounds__(256) k_ip_mix(Fp* out, uint32_t a, int mode, int fmul_iters, int dfma_iters,
+                                                uint32_t dfma_warps) {
+  const bool odd = (dfma_warps >> (threadIdx.x >> 5)) & 1;
+  Fp r = Fp::zero();
+  if (!odd) {
+    if (!(mode & 1)) return;
+    Fp x = Fp::one(), y = Fp::rsquared(), z = Fp::one();
+    x.v[0] += threadIdx.x;
+    z.v[0] += a;
+#pragma unroll 1
+    for (int it = 0; it < fmul_iters; it++) {
+      x = fmul(x, y);
+      z = fmul(z, y);
+      x = fmul(x, z);
+      z = fmul(z, x);
+    }
+    r = fadd(x, z);
+  } else {
+    if (!(mode & 2)) return;
+    Fp x0 = Fp::one(), z0 = Fp::one();
+    x0.v[0] += threadIdx.x;
+    z0.v[0] += a;
+    Fd x = fd_from_fp(x0), y = fd_from_fp(Fp::rsquared()), z = fd_from_fp(z0);
+#pragma unroll 1
+    for (int it = 0; it < dfma_iters; it++) {
+      x = dfmul(x, y);
+      z = dfmul(z, y);
+      x = dfmul(x, z);
+      z = dfmul(z, x);
+    }
+    r = fadd(fd_to_fp(x), fd_to_fp(z));
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 void bench_int_pipe(int kind, double* ops_per_sec, float* ms) {
   int dev = 0, sms = 0;
   G16_CUDA(cudaGetDevice(&dev));
@@ -231,7 +278,9 @@ void bench_int_pipe(int kind, double* ops_per_sec, float* ms) {
     if (kind == 0) k_ip_madlo<<<blocks, threads>>>(out.as<uint32_t>(), 3, 5);
     else if (kind == 1) k_ip_madhi<<<blocks, threads>>>(out.as<uint32_t>(), 0x9e3779b9u, 5);
     else if (kind == 2) k_ip_wide<<<blocks, threads>>>(out.as<uint32_t>(), 0x9e3779b9u, 0x7f4a7c15u);
-    else k_ip_fmul<<<blocks, threads>>>(out.as<Fp>(), 7);
+    else if (kind == 3) k_ip_fmul<<<blocks, threads>>>(out.as<Fp>(), 7);
+    else k_ip_mix<<<blocks, threads>>>(out.as<Fp>(), 7, kind == 4 ? 2 : kind == 5 ? 1 : 3, IP_ITERS / 8, IP_ITERS / 8,
+                                      kind <= 6 ? 0xAAu : kind == 7 ? 0xFFu : kind == 8 ? 0x88u : 0xEEu);
     G16_LAUNCH_CHECK();
   };
   for (int w = 0; w < 2; w++) launch();
@@ -248,7 +297,10 @@ void bench_int_pipe(int kind, double* ops_per_sec, float* ms) {
   double per_thread;
   if (kind == 0 || kind == 1) per_thread = (double)IP_ITERS * 32.0;        // MAC32 per thread
   else if (kind == 2) per_thread = (double)IP_ITERS * 2.0 * 4.0 * 4.0;      // wide MAC32 (lo/hi pair = 1)
-  else per_thread = (double)(IP_ITERS / 8) * 4.0;                            // modmuls
+  else if (kind == 3) per_thread = (double)(IP_ITERS / 8) * 4.0;             // modmuls
+  else if (kind >= 7) per_thread = (double)(IP_ITERS / 8) * 4.0;             // all warps, either multiplier
+  else if (kind == 4) per_thread = (double)(IP_ITERS / 8) * 4.0 * 0.5;       // FP64 modmuls, odd warps only
+  else per_thread = (double)(IP_ITERS / 8) * 4.0 * 0.5;                      // modmuls, even warps only
   double total = per_thread * (double)blocks * threads * reps;
   *ms = t / reps;
   *ops_per_sec = total / ((double)t * 1e-3);

@@ -1,0 +1,7 @@
+import ctypes as C, sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "nim-groth16_b200"))
+from g16b200 import _lib
+lib = _lib.load()
+ops, ms = C.c_double(), C.c_float()
+_lib.check(lib.g16_bench_int_pipe(int(sys.argv[1]), C.byref(ops), C.byref(ms)))
+print(ops.value, ms.value)
