@@ -265,7 +265,9 @@ int g16_selftest(uint32_t seed, uint32_t cases);
  * FP64-pipe co-issue experiment: 4 = DFMA Montgomery multiplies (field_fp64.cuh) on the odd warps only,
  * 5 = IMAD Montgomery multiplies on the even warps only, 6 = both at once (modmuls/s of the even warps; the odd
  * warps do the same number of multiplies -- compare `ms` with kinds 4 and 5); 7 = DFMA multiplies on all warps;
- * 8 / 9 = 2 of 8 / 6 of 8 warps on DFMA, the rest on IMAD (total modmuls/s). */
+ * 8 / 9 = 2 of 8 / 6 of 8 warps on DFMA, the rest on IMAD (total modmuls/s).
+ * Instruction-mix models (multiplies/s): 10 = 128 IMAD.WIDE + 40 IADD3 (today's fmul), 11 = 112 + 152, 12 = 112 + 200.
+ * 13 = Montgomery multiplies without the final conditional subtraction (operands and results in [0, 2p)). */
 int g16_bench_int_pipe(int kind, double* ops_per_sec, float* ms);
 /* number of kernels this library has launched in this process */
 uint64_t g16_kernel_launch_count(void);

@@ -528,7 +528,7 @@ int g16_selftest(uint32_t seed, uint32_t cases) {
 }
 int g16_bench_int_pipe(int kind, double* ops_per_sec, float* ms) {
   return guard([&] {
-    G16_REQUIRE(kind >= 0 && kind <= 9 && ops_per_sec && ms, "bad argument");
+    G16_REQUIRE(kind >= 0 && kind <= 13 && ops_per_sec && ms, "bad argument");
     bench_int_pipe(kind, ops_per_sec, ms);
   });
 }

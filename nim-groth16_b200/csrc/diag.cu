@@ -213,6 +213,19 @@ __global__ void __launch_bounds__(256) k_ip_wide(uint32_t* out, uint32_t a, uint
     for (int i = 0; i < 8; i++) s ^= x[j][i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+__global__ void __launch_bounds__(256) k_ip_fmul_lazy(Fp* out, uint32_t a) {
+  Fp x = Fp::one(), y = Fp::rsquared(), z = Fp::one();
+  x.v[0] += threadIdx.x;
+  z.v[0] += a;
+#pragma unroll 1
+  for (int it = 0; it < IP_ITERS / 8; it++) {
+    x = fmul_core<true>(x, y);
+    z = fmul_core<true>(z, y);
+    x = fmul_core<true>(x, z);
+    z = fmul_core<true>(z, x);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = fadd(x, z);
+}
 __global__ void __launch_bounds__(256) k_ip_fmul(Fp* out, uint32_t a) {
   Fp x = Fp::one(), y = Fp::rsquared(), z = Fp::one();
   x.v[0] += threadIdx.x;
@@ -264,6 +277,48 @@ __global__ void __launch_bounds__(256) k_ip_mix(Fp* out, uint32_t a, int mode, i
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+// Instruction-mix probe for a Karatsuba multiplier: per "multiply" 28 rows of 4 wide MACs (112 IMAD.WIDE instead
+// of 128) plus `adds8` carry chains of 8 IADD3 on the ALU pipe; wide = 32 rows and adds8 = 5 models today's fmul.
+template <int ROWS, int ADDS8>
+__global__ void __launch_bounds__(256) k_ip_kmix(uint32_t* out, uint32_t a, uint32_t b) {
+  uint32_t x[4][8], y[3][8];
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[j][i] = threadIdx.x + i + j;
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) y[j][i] = threadIdx.x * 3 + i + j;
+#if defined(__CUDA_ARCH__)
+  uint32_t p1 = a, p3 = a + 2, p5 = a + 4, p7 = a + 6;
+#pragma unroll 1
+  for (int it = 0; it < IP_ITERS / 4; it++) {
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+      mad_row_nc(x[r & 3], p1, p3, p5, p7, b + r);
+      if ((r * ADDS8) / ROWS != ((r + 1) * ADDS8) / ROWS) {
+        const int k = (r * ADDS8) / ROWS;
+        add8_ip(y[k % 3], x[(r + 2) & 3]);   // consumes a product row like the Karatsuba glue would
+      }
+    }
+  }
+#else
+  (void)a;
+  (void)b;
+#endif
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= x[j][i];
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= y[j][i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 void bench_int_pipe(int kind, double* ops_per_sec, float* ms) {
   int dev = 0, sms = 0;
   G16_CUDA(cudaGetDevice(&dev));
@@ -279,6 +334,10 @@ void bench_int_pipe(int kind, double* ops_per_sec, float* ms) {
     else if (kind == 1) k_ip_madhi<<<blocks, threads>>>(out.as<uint32_t>(), 0x9e3779b9u, 5);
     else if (kind == 2) k_ip_wide<<<blocks, threads>>>(out.as<uint32_t>(), 0x9e3779b9u, 0x7f4a7c15u);
     else if (kind == 3) k_ip_fmul<<<blocks, threads>>>(out.as<Fp>(), 7);
+    else if (kind == 13) k_ip_fmul_lazy<<<blocks, threads>>>(out.as<Fp>(), 7);
+    else if (kind == 10) k_ip_kmix<32, 5><<<blocks, threads>>>(out.as<uint32_t>(), 0x9e3779b9u, 0x7f4a7c15u);
+    else if (kind == 11) k_ip_kmix<28, 19><<<blocks, threads>>>(out.as<uint32_t>(), 0x9e3779b9u, 0x7f4a7c15u);
+    else if (kind == 12) k_ip_kmix<28, 25><<<blocks, threads>>>(out.as<uint32_t>(), 0x9e3779b9u, 0x7f4a7c15u);
     else k_ip_mix<<<blocks, threads>>>(out.as<Fp>(), 7, kind == 4 ? 2 : kind == 5 ? 1 : 3, IP_ITERS / 8, IP_ITERS / 8,
                                       kind <= 6 ? 0xAAu : kind == 7 ? 0xFFu : kind == 8 ? 0x88u : 0xEEu);
     G16_LAUNCH_CHECK();
@@ -298,6 +357,8 @@ void bench_int_pipe(int kind, double* ops_per_sec, float* ms) {
   if (kind == 0 || kind == 1) per_thread = (double)IP_ITERS * 32.0;        // MAC32 per thread
   else if (kind == 2) per_thread = (double)IP_ITERS * 2.0 * 4.0 * 4.0;      // wide MAC32 (lo/hi pair = 1)
   else if (kind == 3) per_thread = (double)(IP_ITERS / 8) * 4.0;             // modmuls
+  else if (kind == 13) per_thread = (double)(IP_ITERS / 8) * 4.0;
+  else if (kind >= 10) per_thread = (double)(IP_ITERS / 4);                   // modelled multiplies
   else if (kind >= 7) per_thread = (double)(IP_ITERS / 8) * 4.0;             // all warps, either multiplier
   else if (kind == 4) per_thread = (double)(IP_ITERS / 8) * 4.0 * 0.5;       // FP64 modmuls, odd warps only
   else per_thread = (double)(IP_ITERS / 8) * 4.0 * 0.5;                      // modmuls, even warps only

@@ -309,8 +309,10 @@ G16_HD Fe<P> fhalve(const Fe<P>& a) {
 // ---------------------------------------------------------------------------------------
 // Montgomery multiplication: returns a*b/2^256 mod p, fully reduced.
 // ---------------------------------------------------------------------------------------
-template <class P>
-G16_HD Fe<P> fmul(const Fe<P>& a, const Fe<P>& b) {
+// LAZY = true skips the final conditional subtraction: for operands < 2p the result is < 2p as well
+// ((2p)^2 / 2^256 + p < 1.76 p because p < 2^254), congruent to a*b/2^256.
+template <bool LAZY, class P>
+G16_HD Fe<P> fmul_core(const Fe<P>& a, const Fe<P>& b) {
   Fe<P> r;
 #if defined(__CUDA_ARCH__)
   // t[0] / t[1] alternate between the "even" (column k) and "odd" (column k+1) roles.
@@ -332,6 +334,7 @@ G16_HD Fe<P> fmul(const Fe<P>& a, const Fe<P>& b) {
   merge8_ip(t[1], t[0]);
 #pragma unroll
   for (int k = 0; k < 8; k++) r.v[k] = t[1][k];
+  if (LAZY) return r;
   Fe<P> u = r;
   uint32_t pm[8];
 #pragma unroll
@@ -367,6 +370,7 @@ G16_HD Fe<P> fmul(const Fe<P>& a, const Fe<P>& b) {
     t[8] = t[9] + (uint32_t)(c >> 32);
   }
   for (int k = 0; k < 8; k++) r.v[k] = t[k];
+  if (LAZY) return r;
   Fe<P> u;
   int64_t bw = 0;
   for (int k = 0; k < 8; k++) {
@@ -376,6 +380,10 @@ G16_HD Fe<P> fmul(const Fe<P>& a, const Fe<P>& b) {
   }
   return (bw && !t[8]) ? r : u;
 #endif
+}
+template <class P>
+G16_HD Fe<P> fmul(const Fe<P>& a, const Fe<P>& b) {
+  return fmul_core<false>(a, b);
 }
 
 // Two independent Montgomery products with their carry chains interleaved row by row: the rows of one

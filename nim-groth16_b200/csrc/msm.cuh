@@ -29,12 +29,15 @@ struct MsmGeometry {
   size_t m = 0;            // (scalar, window) pairs = nwin * n
   uint32_t T = 0;          // maximum additions per work item
   uint32_t max_items = 0;  // upper bound on work items
+  int tree_log = 0;        // 0: XYZZ work items; 3..6: batched-affine tree over chunks of 2^tree_log slots (T)
 };
+constexpr int MSM_TREE_MAX_LOG = 6;
 
 constexpr uint32_t MSM_FIXUP_SMALL_MAX = 16;   // buckets with at most this many items are merged by one thread
 
 int msm_pick_window(size_t n, bool precomp);
-MsmGeometry msm_geometry(size_t n, int c, bool precomp);
+// tree_log < 0: take the library default (environment G16_MSM_TREE, 0 = XYZZ work items)
+MsmGeometry msm_geometry(size_t n, int c, bool precomp, int tree_log = -1);
 
 class MsmSorter {
  public:
@@ -53,10 +56,18 @@ class MsmSorter {
   const uint32_t* items_sorted() const { return item_idx_[1].as<uint32_t>(); }
   // buckets split into several items: [count_small, count_big, small[nbuckets], big[nbuckets]]
   const uint32_t* multi() const { return multi_.as<uint32_t>(); }
+  // batched-affine tree (geom().tree_log > 0): per round r the list of left slots (bit 31: no partner, round 0
+  // only) and its length; the lists depend only on the bucket structure
+  const uint32_t* tree_list(int r) const { return tree_list_.as<uint32_t>() + tree_off_[r]; }
+  const uint32_t* tree_count(int r) const { return tree_cnt_.as<uint32_t>() + r; }
+  uint32_t tree_cap(int r) const { return tree_cap_[r]; }
 
  private:
   MsmGeometry g_;
   DevBuf keys_[2], vals_[2], start_, chunks_, item_start_, item_bucket_, item_key_[2], item_idx_[2], multi_, cub_tmp_;
+  DevBuf tree_list_, tree_cnt_;
+  size_t tree_off_[MSM_TREE_MAX_LOG] = {0, 0, 0, 0, 0, 0};
+  uint32_t tree_cap_[MSM_TREE_MAX_LOG] = {0, 0, 0, 0, 0, 0};
 };
 
 template <class F>
@@ -78,7 +89,10 @@ class MsmAccumulator {
   float last_accum_ms() const;
 
  private:
+  void run_tree(const MsmSorter& sorter, const MsmPointSet<F>* sets, int nsets, XYZZ<F>* const* buckets,
+                cudaStream_t stream);
   DevBuf buckets_, partials_, winpart_;
+  DevBuf tree_w_, tree_m_, tree_nodes_, tree_bp_;
   cudaEvent_t pev_[2] = {nullptr, nullptr};
 };
 

@@ -15,6 +15,7 @@
 #include "msm.cuh"
 #include <stdlib.h>
 #include "msm_digits.cuh"
+#include "msm_tree.cuh"
 
 #ifndef G16_G2_MINB_DEFAULT
 #define G16_G2_MINB_DEFAULT 3
@@ -340,7 +341,8 @@ MsmAccumulator<F>::~MsmAccumulator() {
 }
 template <class F>
 size_t MsmAccumulator<F>::workspace_bytes() const {
-  return buckets_.bytes + partials_.bytes + winpart_.bytes;
+  return buckets_.bytes + partials_.bytes + winpart_.bytes + tree_w_.bytes + tree_m_.bytes + tree_nodes_.bytes +
+         tree_bp_.bytes;
 }
 template <class F>
 float MsmAccumulator<F>::last_accum_ms() const {
@@ -368,6 +370,57 @@ static void launch_accumulate(dim3 grid, cudaStream_t stream, const AccSets<F>& 
     else k_bucket_accumulate<F, 3><<<grid, 128, 0, stream>>>(G16_ACC_ARGS);   // 168 registers, a few spills: 6.9 vs 7.3 ms
   }
 #undef G16_ACC_ARGS
+}
+
+// batched-affine bucket accumulation (msm_tree.cuh): tree_log rounds of three launches, then the chunk heads
+// become the bucket sums
+template <class F>
+void MsmAccumulator<F>::run_tree(const MsmSorter& sorter, const MsmPointSet<F>* in, int nsets,
+                                 XYZZ<F>* const* buckets, cudaStream_t stream) {
+  const MsmGeometry& g = sorter.geom();
+  const size_t cap0 = sorter.tree_cap(0);
+  const size_t blocks0 = (cap0 + TREE_PER_BLOCK - 1) / TREE_PER_BLOCK;
+  const size_t w_bytes = g.m * sizeof(Affine<F>);
+  const size_t m_bytes = cap0 * sizeof(F);
+  const size_t n_bytes = blocks0 * 2 * TREE_TPB * sizeof(F);
+  const size_t b_bytes = blocks0 * sizeof(F);
+  tree_w_.ensure(w_bytes * nsets);
+  tree_m_.ensure(m_bytes * nsets);
+  tree_nodes_.ensure(n_bytes * nsets);
+  tree_bp_.ensure(2 * b_bytes * nsets);
+  TreeSets<F> ts;
+  for (int s = 0; s < MAX_SETS; s++) {
+    int k = s < nsets ? s : 0;
+    ts.points[s] = in[k].points;
+    ts.W[s] = reinterpret_cast<Affine<F>*>(tree_w_.as<char>() + w_bytes * k);
+    ts.M[s] = reinterpret_cast<F*>(tree_m_.as<char>() + m_bytes * k);
+    ts.tree[s] = reinterpret_cast<F*>(tree_nodes_.as<char>() + n_bytes * k);
+    ts.bp[s] = reinterpret_cast<F*>(tree_bp_.as<char>() + 2 * b_bytes * k);
+    ts.ibp[s] = reinterpret_cast<F*>(tree_bp_.as<char>() + 2 * b_bytes * k + b_bytes);
+    ts.buckets[s] = buckets[k];
+  }
+  for (int r = 0; r < g.tree_log; r++) {
+    dim3 grid(div_up(sorter.tree_cap(r), TREE_PER_BLOCK), (unsigned)nsets);
+    if (r == 0)
+      k_tree_prepare<F, true><<<grid, TREE_TPB, 0, stream>>>(ts, sorter.vals(), sorter.tree_list(r), sorter.tree_count(r), r);
+    else
+      k_tree_prepare<F, false><<<grid, TREE_TPB, 0, stream>>>(ts, sorter.vals(), sorter.tree_list(r), sorter.tree_count(r), r);
+    G16_LAUNCH_CHECK();
+    k_tree_invert<F><<<nsets, TREE_TPB, 0, stream>>>(ts, sorter.tree_count(r));
+    G16_LAUNCH_CHECK();
+    k_tree_finish<F><<<grid, TREE_TPB, 0, stream>>>(ts, sorter.tree_list(r), sorter.tree_count(r), r);
+    G16_LAUNCH_CHECK();
+  }
+  dim3 bgrid(div_up(g.nbuckets, 128), (unsigned)nsets);
+  k_tree_finalize<F><<<bgrid, 128, 0, stream>>>(ts, sorter.start(), sorter.item_start(), g.nbuckets);
+  G16_LAUNCH_CHECK();
+  k_tree_fixup_small<F><<<bgrid, 128, 0, stream>>>(ts, sorter.start(), sorter.item_start(), sorter.multi(),
+                                                    g.tree_log);
+  G16_LAUNCH_CHECK();
+  dim3 fgrid(148, (unsigned)nsets);
+  k_tree_fixup_big<F><<<fgrid, 128, 128 * sizeof(XYZZ<F>), stream>>>(ts, sorter.start(), sorter.item_start(),
+                                                                     sorter.multi(), g.nbuckets, g.tree_log);
+  G16_LAUNCH_CHECK();
 }
 
 template <class F>
@@ -401,7 +454,7 @@ void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, i
   }
 
   size_t bucket_bytes = (size_t)g.nbuckets * sizeof(XYZZ<F>);
-  size_t partial_bytes = (size_t)g.max_items * sizeof(XYZZ<F>);
+  size_t partial_bytes = g.tree_log ? 0 : (size_t)g.max_items * sizeof(XYZZ<F>);
   size_t winpart_bytes = (s_entries + r_entries + nsetsB) * sizeof(XYZZ<F>);
   buckets_.ensure(bucket_bytes * nsets);
   partials_.ensure(partial_bytes * nsets);
@@ -422,17 +475,22 @@ void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, i
       if (!pev_[i]) G16_CUDA(cudaEventCreate(&pev_[i]));
     G16_CUDA(cudaEventRecord(pev_[0], stream));
   }
-  dim3 agrid(div_up(g.max_items, 128), (unsigned)nsets);
-  launch_accumulate<F>(agrid, stream, sets, sorter, g);
-  G16_LAUNCH_CHECK();
-  if (profile) G16_CUDA(cudaEventRecord(pev_[1], stream));
-  dim3 sgrid(div_up(g.nbuckets, 128), (unsigned)nsets);
-  k_bucket_fixup_small<F><<<sgrid, 128, 0, stream>>>(sets, sorter.item_start(), sorter.multi());
-  G16_LAUNCH_CHECK();
-  dim3 fgrid(148, (unsigned)nsets);
-  k_bucket_fixup<F><<<fgrid, 128, 128 * sizeof(XYZZ<F>), stream>>>(sets, sorter.item_start(), sorter.multi(),
-                                                                   g.nbuckets);
-  G16_LAUNCH_CHECK();
+  if (g.tree_log) {
+    run_tree(sorter, in, nsets, sets.buckets, stream);
+    if (profile) G16_CUDA(cudaEventRecord(pev_[1], stream));
+  } else {
+    dim3 agrid(div_up(g.max_items, 128), (unsigned)nsets);
+    launch_accumulate<F>(agrid, stream, sets, sorter, g);
+    G16_LAUNCH_CHECK();
+    if (profile) G16_CUDA(cudaEventRecord(pev_[1], stream));
+    dim3 sgrid(div_up(g.nbuckets, 128), (unsigned)nsets);
+    k_bucket_fixup_small<F><<<sgrid, 128, 0, stream>>>(sets, sorter.item_start(), sorter.multi());
+    G16_LAUNCH_CHECK();
+    dim3 fgrid(148, (unsigned)nsets);
+    k_bucket_fixup<F><<<fgrid, 128, 128 * sizeof(XYZZ<F>), stream>>>(sets, sorter.item_start(), sorter.multi(),
+                                                                     g.nbuckets);
+    G16_LAUNCH_CHECK();
+  }
   // bucket reduction: one launch per level, then the per-set Horner over the levels
   ReduceFinal<F> fin;
   fin.nlevels = nlevels;

@@ -12,6 +12,11 @@
 #include <cub/device/device_scan.cuh>
 #include "msm.cuh"
 #include "msm_digits.cuh"
+#include <stdlib.h>
+
+#ifndef G16_MSM_TREE_DEFAULT
+#define G16_MSM_TREE_DEFAULT 0
+#endif
 
 namespace g16 {
 
@@ -35,7 +40,17 @@ int msm_pick_window(size_t n, bool precomp) {
   return best_c;
 }
 
-MsmGeometry msm_geometry(size_t n, int c, bool precomp) {
+static int default_tree_log() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("G16_MSM_TREE");
+    v = e ? atoi(e) : G16_MSM_TREE_DEFAULT;
+    if (v != 0 && (v < 3 || v > MSM_TREE_MAX_LOG)) v = 0;
+  }
+  return v;
+}
+
+MsmGeometry msm_geometry(size_t n, int c, bool precomp, int tree_log) {
   G16_REQUIRE(n < ((size_t)1 << 31), "MSM size must be below 2^31");
   G16_REQUIRE(c >= 2 && c <= 22, "MSM window must be 2..22 bits");
   MsmGeometry g;
@@ -58,6 +73,8 @@ MsmGeometry msm_geometry(size_t n, int c, bool precomp) {
   size_t T = g.m / 150000;
   if (T < 2 * avg + 16) T = 2 * avg + 16;
   if (T > 32768) T = 32768;
+  g.tree_log = tree_log < 0 ? default_tree_log() : tree_log;
+  if (g.tree_log) T = (size_t)1 << g.tree_log;   // chunks of the batched-affine tree (msm_tree.cuh)
   g.T = (uint32_t)T;
   g.max_items = g.nbuckets + (uint32_t)(g.m / T) + 1;
   return g;
@@ -154,12 +171,96 @@ __global__ void k_make_items(const uint32_t* __restrict__ start, const uint32_t*
   }
 }
 
+// Lists of the additions of every tree round (msm_tree.cuh): slot j with chunk-relative position q is a left
+// operand of round r when q is a multiple of 2^(r+1) and q + 2^r is still inside the chunk.  Round 0 also lists
+// the last element of odd-length chunks (bit 31: no partner) so that it is copied into the working array.
+constexpr int TREE_LIST_TPB = 1024;
+constexpr int TREE_LIST_SPT = 4;      // slots per thread
+struct TreeListOffsets {
+  size_t off[MSM_TREE_MAX_LOG];
+};
+__global__ void __launch_bounds__(TREE_LIST_TPB) k_tree_lists(const uint32_t* __restrict__ keys,
+                                                              const uint32_t* __restrict__ start, uint32_t m,
+                                                              uint32_t nbuckets, int tree_log,
+                                                              uint32_t* __restrict__ lists, TreeListOffsets offs,
+                                                              uint32_t* __restrict__ cnt) {
+  // one global atomic per block and round: counts per warp -> block scan in shared memory -> base
+  __shared__ uint32_t warp_cnt[MSM_TREE_MAX_LOG][TREE_LIST_TPB / 32];
+  __shared__ uint32_t block_base[MSM_TREE_MAX_LOG];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t T = 1u << tree_log;
+  uint32_t q[TREE_LIST_SPT], lc[TREE_LIST_SPT];
+  const uint32_t j0 = (blockIdx.x * TREE_LIST_TPB + threadIdx.x) * TREE_LIST_SPT;
+#pragma unroll
+  for (int k = 0; k < TREE_LIST_SPT; k++) {
+    const uint32_t j = j0 + k;
+    q[k] = 1;        // odd position with an empty chunk: never listed
+    lc[k] = 0;
+    if (j < m) {
+      uint32_t b = keys[j];
+      if (b < nbuckets) {
+        uint32_t s0 = start[b];
+        uint32_t rel = j - s0, len = start[b + 1] - s0;
+        q[k] = rel & (T - 1u);
+        lc[k] = len - (rel - q[k]);
+        if (lc[k] > T) lc[k] = T;
+      }
+    }
+  }
+  // pass 1: counts
+  uint32_t mine[MSM_TREE_MAX_LOG];
+#pragma unroll
+  for (int r = 0; r < MSM_TREE_MAX_LOG; r++) {
+    uint32_t c = 0;
+    if (r < tree_log) {
+#pragma unroll
+      for (int k = 0; k < TREE_LIST_SPT; k++) {
+        bool left = lc[k] && (q[k] & ((2u << r) - 1u)) == 0;
+        c += (left && (r == 0 || q[k] + (1u << r) < lc[k])) ? 1u : 0u;
+      }
+    }
+    mine[r] = c;
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if ((int)lane >= d) incl += o;
+    }
+    if (lane == 31) warp_cnt[r][warp] = incl;
+    mine[r] = incl - c;     // exclusive prefix inside the warp
+  }
+  __syncthreads();
+  if (threadIdx.x < (unsigned)tree_log) {
+    const int r = threadIdx.x;
+    uint32_t run = 0;
+    for (int w = 0; w < TREE_LIST_TPB / 32; w++) {
+      uint32_t c = warp_cnt[r][w];
+      warp_cnt[r][w] = run;
+      run += c;
+    }
+    block_base[r] = run ? atomicAdd(cnt + r, run) : 0u;
+  }
+  __syncthreads();
+  // pass 2: write
+  for (int r = 0; r < tree_log; r++) {
+    uint32_t pos = block_base[r] + warp_cnt[r][warp] + mine[r];
+    uint32_t* out = lists + offs.off[r];
+#pragma unroll
+    for (int k = 0; k < TREE_LIST_SPT; k++) {
+      bool left = lc[k] && (q[k] & ((2u << r) - 1u)) == 0;
+      bool pair = left && (q[k] + (1u << r) < lc[k]);
+      if (pair || (r == 0 && left)) out[pos++] = (j0 + k) | (pair ? 0u : 0x80000000u);
+    }
+  }
+}
+
 MsmSorter::~MsmSorter() {}
 
 size_t MsmSorter::workspace_bytes() const {
   size_t t = 0;
   const DevBuf* all[] = {&keys_[0], &keys_[1], &vals_[0], &vals_[1], &start_, &chunks_, &item_start_, &item_bucket_,
-                         &item_key_[0], &item_key_[1], &item_idx_[0], &item_idx_[1], &multi_, &cub_tmp_};
+                         &item_key_[0], &item_key_[1], &item_idx_[0], &item_idx_[1], &multi_, &cub_tmp_,
+                         &tree_list_, &tree_cnt_};
   for (auto* b : all) t += b->bytes;
   return t;
 }
@@ -227,9 +328,28 @@ void MsmSorter::run(const Fr* scalars, bool scalars_mont, const MsmGeometry& g, 
                                                             g.nbuckets, g.T, item_bucket_.as<uint32_t>(),
                                                             item_key_[0].as<uint32_t>(), multi_.as<uint32_t>());
   G16_LAUNCH_CHECK();
-  G16_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp_.p, t3, item_key_[0].as<uint32_t>(), item_key_[1].as<uint32_t>(),
-                                           item_idx_[0].as<uint32_t>(), item_idx_[1].as<uint32_t>(),
-                                           (int64_t)g.max_items, 0, item_bits, stream));
+  if (!g.tree_log) {
+    G16_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp_.p, t3, item_key_[0].as<uint32_t>(), item_key_[1].as<uint32_t>(),
+                                             item_idx_[0].as<uint32_t>(), item_idx_[1].as<uint32_t>(),
+                                             (int64_t)g.max_items, 0, item_bits, stream));
+    return;
+  }
+  // batched-affine tree: per-round addition lists
+  size_t total = 0;
+  for (int r = 0; r < MSM_TREE_MAX_LOG; r++) {
+    tree_off_[r] = total;
+    tree_cap_[r] = r < g.tree_log ? (uint32_t)((m >> (r + 1)) + g.max_items + 32) : 0;
+    total += tree_cap_[r];
+  }
+  tree_list_.ensure(total * 4);
+  tree_cnt_.ensure(MSM_TREE_MAX_LOG * 4);
+  G16_CUDA(cudaMemsetAsync(tree_cnt_.p, 0, MSM_TREE_MAX_LOG * 4, stream));
+  TreeListOffsets offs;
+  for (int r = 0; r < MSM_TREE_MAX_LOG; r++) offs.off[r] = tree_off_[r];
+  k_tree_lists<<<div_up(m, TREE_LIST_TPB * TREE_LIST_SPT), TREE_LIST_TPB, 0, stream>>>(
+      keys_[1].as<uint32_t>(), start_.as<uint32_t>(), (uint32_t)m, g.nbuckets, g.tree_log,
+      tree_list_.as<uint32_t>(), offs, tree_cnt_.as<uint32_t>());
+  G16_LAUNCH_CHECK();
 }
 
 }  // namespace g16

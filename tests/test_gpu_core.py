@@ -242,3 +242,22 @@ def test_msm_resident_table_layout(g, lg, g2):
         plain = (g.msm_multi_threaded_g2 if g2 else g.msm_multi_threaded_g1)(0, sc, pts, form=E.FORM_STD)
         assert np.array_equal(plain, out)
     lib.g16_msm_plan_destroy(plan)
+
+
+def test_msm_batched_affine_tree_mode_matches():
+    """The experimental batched-affine bucket accumulation (msm_tree.cuh, G16_MSM_TREE=5: read once per process)
+    must give the same bit-exact answers: rerun the MSM and prover parity tests in a child process in that mode."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("G16_MSM_TREE"):
+        pytest.skip("already running in tree mode")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, G16_MSM_TREE="5")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-k",
+                        "msm_edge_cases or msm_resident_table_layout or msm_g2_vs_oracle_naive or reference_circuit_golden or "
+                        "synthetic_circuit_closed_form or sharded_contexts_recombine",
+                        os.path.join(root, "tests", "test_gpu_core.py"), os.path.join(root, "tests", "test_gpu_prover.py")],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
