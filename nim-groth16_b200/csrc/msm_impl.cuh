@@ -8,7 +8,9 @@
 //   k_bucket_accumulate  one thread per work item (<= T mixed additions, items sorted by length), gathered
 //                        affine loads (16-byte vectors), XYZZ accumulator in registers
 //   k_bucket_fixup       buckets that were split into several items: block-wide tree sum of their partials
-//   k_reduce_level/final sum_k (k+1) B_k per bucket set as a recursion over levels of running sums
+//   k_reduce_level       sum_k (k+1) B_k per bucket set, level 1: running sums over 16 consecutive buckets
+//   k_reduce_bits/final  the 16-times shorter array left by level 1, summed bit by bit of the index (3 launches
+//                        in total instead of a chain of latency-bound levels)
 //   k_window_combine     Horner over the windows (plain layout; a single window in the precomputed layout)
 //   k_build_table        precomputed layout: 2^(c w) P_i for every window, batch-normalised to affine
 #pragma once
@@ -146,13 +148,12 @@ __global__ void __launch_bounds__(128) k_bucket_fixup(AccSets<F> sets, const uin
 }
 
 // ---------------------------------------------------------------------------------------
-// bucket reduction: per bucket set, sum_k (k+1) * B_k, as a recursion over levels.
+// bucket reduction: per bucket set, sum_k (k+1) * B_k.
 //   level 1: thread t owns L consecutive buckets; running sums give S_t = sum_j B_{tL+j} and
-//            R_t = sum_j (j+1) B_{tL+j}.  Then sum_k (k+1) B_k = sum_t R_t + L * sum_t t * S_t,
-//   and sum_t t * S_t is the same problem on the L-times shorter array S with 0-based weights (level 2, ...).
-//   Result = R^(1) + L * (R^(2) + L * (R^(3) + ...)),  R^(l) = plain sum of the level's local weighted sums.
-// No per-thread scalar multiplication; each level is one launch and the tiny upper levels overlap with the
-// other streams' work.   grid = (blocks, bucket sets (windows), point sets)
+//            R_t = sum_j (j+1) B_{tL+j}.  Then sum_k (k+1) B_k = sum_t R_t + L * sum_t t * S_t.
+//   sum_t t * S_t is the same problem on the L-times shorter array S with 0-based weights; it is summed bit by
+//   bit of t (k_reduce_bits) and k_reduce_final assembles  R + L * sum_j 2^j U_j.
+// No per-thread scalar multiplication.   grid = (blocks, bucket sets (windows), point sets)
 // ---------------------------------------------------------------------------------------
 template <class F>
 struct ReduceLevel {
@@ -160,7 +161,8 @@ struct ReduceLevel {
   XYZZ<F>* out_s[MsmAccumulator<F>::MAX_SETS];       // n_in / L entries per bucket set (input of the next level)
   XYZZ<F>* out_r[MsmAccumulator<F>::MAX_SETS];       // gridDim.x block sums of R per bucket set
   uint32_t n_in, L;
-  int weight_one_based;                              // level 1: weights j+1; upper levels: weights j
+  uint32_t out_r_stride;                             // entries between the R partials of consecutive bucket sets
+  int weight_one_based;                              // level 1: weights j+1; level 2: weights j
 };
 
 template <class F>
@@ -191,51 +193,133 @@ __global__ void __launch_bounds__(128) k_reduce_level(ReduceLevel<F> a) {
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) st_vec(a.out_r[set] + (size_t)w * gridDim.x + blockIdx.x, sum);
+  if (threadIdx.x == 0) st_vec(a.out_r[set] + (size_t)w * a.out_r_stride + blockIdx.x, sum);
 }
 
-constexpr int MSM_MAX_LEVELS = 12;
+// The array S left by the running-sum levels (n entries, 0-based weights t) is not reduced by further levels --
+// they are chains of tiny latency-bound launches on the critical path of every MSM -- but bit by bit:
+//   sum_t t * S_t = sum_j 2^j * U_j,   U_j = sum of the S_t whose index has bit j set.
+// k_reduce_bits: block (j, chunk of 1024 entries) -> one partial of U_j.  grid = (nbits * nchunks, bucket sets,
+// point sets).  About log2(n)/2 additions per entry instead of 2, all of them independent.
+// Partials of the "small levels" (R of level 2, then U_0 .. U_{nbits-1}) live in one array indexed
+// [(bucket set * nsmall + level) * stride + k].
+template <class F>
+struct ReduceBits {
+  const XYZZ<F>* in[MsmAccumulator<F>::MAX_SETS];    // n entries per bucket set
+  XYZZ<F>* out[MsmAccumulator<F>::MAX_SETS];         // small-level array
+  uint32_t n, nbits, nchunks, nsmall, first_level, stride;
+};
+constexpr uint32_t REDUCE_BITS_CHUNK = 1024;
+
+template <class F>
+__global__ void __launch_bounds__(128) k_reduce_bits(ReduceBits<F> a) {
+  extern __shared__ uint4 red_raw[];
+  XYZZ<F>* red = reinterpret_cast<XYZZ<F>*>(red_raw);
+  const uint32_t chunk = blockIdx.x % a.nchunks, j = blockIdx.x / a.nchunks;
+  const uint32_t w = blockIdx.y;
+  const int set = blockIdx.z;
+  const uint32_t base = chunk * REDUCE_BITS_CHUNK;
+  XYZZ<F>* dst = a.out[set] + ((size_t)w * a.nsmall + a.first_level + j) * a.stride + chunk;
+  if ((1u << j) >= REDUCE_BITS_CHUNK && !((base >> j) & 1u)) {   // bit j is constant over the chunk, and clear
+    if (threadIdx.x == 0) st_vec(dst, xyzz_inf<F>());
+    return;
+  }
+  const XYZZ<F>* S = a.in[set] + (size_t)w * a.n;
+  XYZZ<F> acc = xyzz_inf<F>();
+  for (uint32_t k = 0; k < REDUCE_BITS_CHUNK / 128; k++) {
+    const uint32_t t = base + k * 128 + threadIdx.x;
+    if (t < a.n && ((t >> j) & 1u)) {
+      XYZZ<F> o = ld_vec(S + t);
+      xyzz_add_ni(acc, acc, o);
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      XYZZ<F> o = red[threadIdx.x + s];
+      xyzz_add_ni(acc, acc, o);
+      red[threadIdx.x] = acc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_vec(dst, acc);
+}
+
+// total of one bucket set = R1 + sum over the small levels of 2^shift * (sum of the level's partials).
+// grid = (bucket sets, point sets), 128 threads: 48 sum the R1 partials, 4 per small level sum its partials;
+// the doublings of the levels run in parallel, a tree adds the levels.
+constexpr uint32_t REDUCE_FINAL_RTHREADS = 48;
+constexpr uint32_t REDUCE_MAX_SMALL = 20;
 template <class F>
 struct ReduceFinal {
-  const XYZZ<F>* r[MsmAccumulator<F>::MAX_SETS][MSM_MAX_LEVELS];   // block sums of each level
-  XYZZ<F>* wintot[MsmAccumulator<F>::MAX_SETS];                    // one total per bucket set (window)
-  uint32_t blocks[MSM_MAX_LEVELS];
-  uint32_t logL[MSM_MAX_LEVELS];
-  int nlevels;
+  const XYZZ<F>* r1[MsmAccumulator<F>::MAX_SETS];
+  const XYZZ<F>* small[MsmAccumulator<F>::MAX_SETS];
+  XYZZ<F>* wintot[MsmAccumulator<F>::MAX_SETS];
+  uint32_t blocks1, nsmall, stride;
+  uint8_t shift[REDUCE_MAX_SMALL];
+  uint16_t count[REDUCE_MAX_SMALL];
 };
 
-// total of one bucket set: Horner over the levels; grid = (bucket sets, point sets), 128 threads
 template <class F>
 __global__ void __launch_bounds__(128) k_reduce_final(ReduceFinal<F> a) {
   extern __shared__ uint4 red_raw[];
   XYZZ<F>* red = reinterpret_cast<XYZZ<F>*>(red_raw);
   const uint32_t w = blockIdx.x;
   const int set = blockIdx.y;
-  XYZZ<F> total = xyzz_inf<F>();          // only meaningful in thread 0
-  for (int l = a.nlevels - 1; l >= 0; l--) {
-    XYZZ<F> acc = xyzz_inf<F>();
-    for (uint32_t k = threadIdx.x; k < a.blocks[l]; k += blockDim.x) {
-      XYZZ<F> o = ld_vec(a.r[set][l] + (size_t)w * a.blocks[l] + k);
+  const uint32_t tid = threadIdx.x;
+  uint32_t seg_base, local, width;
+  XYZZ<F> acc = xyzz_inf<F>();
+  if (tid < REDUCE_FINAL_RTHREADS) {
+    seg_base = 0;
+    local = tid;
+    width = REDUCE_FINAL_RTHREADS;
+    for (uint32_t k = local; k < a.blocks1; k += REDUCE_FINAL_RTHREADS) {
+      XYZZ<F> o = ld_vec(a.r1[set] + (size_t)w * a.blocks1 + k);
       xyzz_add_ni(acc, acc, o);
     }
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
-      if (threadIdx.x < s) {
-        XYZZ<F> o = red[threadIdx.x + s];
+  } else {
+    const uint32_t l = (tid - REDUCE_FINAL_RTHREADS) >> 2;
+    seg_base = REDUCE_FINAL_RTHREADS + 4 * l;
+    local = (tid - REDUCE_FINAL_RTHREADS) & 3u;
+    width = 4;
+    if (l < a.nsmall)
+      for (uint32_t k = local; k < a.count[l]; k += 4) {
+        XYZZ<F> o = ld_vec(a.small[set] + ((size_t)w * a.nsmall + l) * a.stride + k);
         xyzz_add_ni(acc, acc, o);
-        red[threadIdx.x] = acc;
       }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      // total = R^(l) + L_l * total   (the levels above act through the weights of this level)
-      for (uint32_t j = 0; j < a.logL[l]; j++) xyzz_dbl_ni(total, total);
-      xyzz_add_ni(total, total, acc);
+  }
+  red[tid] = acc;
+  __syncthreads();
+  for (uint32_t s = 32; s > 0; s >>= 1) {
+    if (local < s && local + s < width) {
+      XYZZ<F> o = red[seg_base + local + s];
+      xyzz_add_ni(acc, acc, o);
+      red[tid] = acc;
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) st_vec(a.wintot[set] + w, total);
+  const XYZZ<F> rsum = acc;                   // meaningful in thread 0
+  XYZZ<F> v = xyzz_inf<F>();
+  if (tid < a.nsmall) {
+    v = red[REDUCE_FINAL_RTHREADS + 4 * tid];
+    for (uint32_t i = 0; i < a.shift[tid]; i++) xyzz_dbl_ni(v, v);
+  }
+  __syncthreads();
+  red[tid] = v;
+  __syncthreads();
+  for (uint32_t s = 16; s > 0; s >>= 1) {
+    if (tid < s && tid + s < a.nsmall) {
+      XYZZ<F> o = red[tid + s];
+      xyzz_add_ni(v, v, o);
+      red[tid] = v;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    xyzz_add_ni(v, v, rsum);
+    st_vec(a.wintot[set] + w, v);
+  }
 }
 
 // result = sum_w 2^(c w) * W_w  (Horner from the top window; one window in the precomputed layout)
@@ -428,34 +512,32 @@ void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, i
   G16_REQUIRE(nsets >= 1 && nsets <= MAX_SETS, "MsmAccumulator: 1..3 point sets");
   const MsmGeometry& g = sorter.geom();
   G16_REQUIRE(g.nwin <= MSM_MAX_WINDOWS, "too many windows");
-  // reduction levels: n_0 = nb buckets; level l maps n_l entries to n_l / L_l entries, down to one
+  // bucket reduction plan: running sums over 16 consecutive buckets (level 1), over 8 consecutive entries of the
+  // result when it is still long (level 2), then the bit-sliced sum of what is left
   const uint32_t nsetsB = g.precomp ? 1u : (uint32_t)g.nwin;
-  int nlevels = 0;
-  uint32_t lvl_n[MSM_MAX_LEVELS + 1], lvl_L[MSM_MAX_LEVELS], lvl_tpb[MSM_MAX_LEVELS], lvl_blocks[MSM_MAX_LEVELS];
-  lvl_n[0] = g.nb;
-  while (lvl_n[nlevels] > 1) {
-    G16_REQUIRE(nlevels < MSM_MAX_LEVELS, "too many reduction levels");
-    // level 1 is throughput-bound (fan-in 16 keeps its work at 2.1 additions per bucket); the upper levels are
-    // latency-bound chains of tiny launches, so they use fan-in 4 (7 sequential additions per level)
-    uint32_t want = nlevels == 0 ? 16u : 4u;
-    uint32_t L = lvl_n[nlevels] >= want ? want : lvl_n[nlevels];
-    uint32_t threads = lvl_n[nlevels] / L;
-    lvl_L[nlevels] = L;
-    lvl_tpb[nlevels] = threads < 128u ? (threads < 32u ? 32u : threads) : 128u;
-    lvl_blocks[nlevels] = (threads + lvl_tpb[nlevels] - 1) / lvl_tpb[nlevels];
-    lvl_n[nlevels + 1] = threads;
-    nlevels++;
-  }
-  // scratch per point set: the S array and the block sums of every level, then one total per bucket set
-  size_t s_entries = 0, r_entries = 0;
-  for (int l = 0; l < nlevels; l++) {
-    s_entries += (size_t)nsetsB * lvl_n[l + 1];
-    r_entries += (size_t)nsetsB * lvl_blocks[l];
-  }
+  auto ilog2 = [](uint32_t v) { uint32_t l = 0; while ((1u << l) < v) l++; return l; };
+  auto tpb_for = [](uint32_t threads) { return threads < 128u ? (threads < 32u ? 32u : threads) : 128u; };
+  const uint32_t L1 = g.nb >= 16u ? 16u : g.nb;
+  const uint32_t n1 = g.nb / L1;
+  const uint32_t L2 = n1 >= 8192u ? 8u : 1u;                     // level 2 only pays for itself on long arrays
+  const uint32_t n2 = n1 / L2;
+  const uint32_t tpb1 = tpb_for(n1), blocks1 = (n1 + tpb1 - 1) / tpb1;
+  const uint32_t tpb2 = tpb_for(n2), blocks2 = L2 > 1 ? (n2 + tpb2 - 1) / tpb2 : 0;
+  const uint32_t nbits = ilog2(n2);
+  const uint32_t nchunks = (n2 + REDUCE_BITS_CHUNK - 1) / REDUCE_BITS_CHUNK;
+  const uint32_t first_bit_level = L2 > 1 ? 1u : 0u;
+  const uint32_t nsmall = first_bit_level + nbits;
+  const uint32_t stride = blocks2 > nchunks ? blocks2 : nchunks;
+  G16_REQUIRE(nsmall <= REDUCE_MAX_SMALL, "too many buckets for the reduction");
+  // scratch per point set: S1 | S2 | R1 partials | small-level partials | one total per bucket set
+  const size_t s1_entries = (size_t)nsetsB * n1;
+  const size_t s2_entries = L2 > 1 ? (size_t)nsetsB * n2 : 0;
+  const size_t r_entries = (size_t)nsetsB * blocks1;
+  const size_t u_entries = (size_t)nsetsB * nsmall * stride;
 
   size_t bucket_bytes = (size_t)g.nbuckets * sizeof(XYZZ<F>);
   size_t partial_bytes = g.tree_log ? 0 : (size_t)g.max_items * sizeof(XYZZ<F>);
-  size_t winpart_bytes = (s_entries + r_entries + nsetsB) * sizeof(XYZZ<F>);
+  size_t winpart_bytes = (s1_entries + s2_entries + r_entries + u_entries + nsetsB) * sizeof(XYZZ<F>);
   buckets_.ensure(bucket_bytes * nsets);
   partials_.ensure(partial_bytes * nsets);
   winpart_.ensure(winpart_bytes * nsets);
@@ -491,41 +573,66 @@ void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, i
                                                                      g.nbuckets);
     G16_LAUNCH_CHECK();
   }
-  // bucket reduction: one launch per level, then the per-set Horner over the levels
+  // bucket reduction: three or four launches
+  const size_t off_s2 = s1_entries, off_r = s1_entries + s2_entries, off_u = off_r + r_entries, off_t = off_u + u_entries;
+  ReduceLevel<F> lv1, lv2;
+  lv1.n_in = g.nb;
+  lv1.L = L1;
+  lv1.out_r_stride = blocks1;
+  lv1.weight_one_based = 1;
+  lv2.n_in = n1;
+  lv2.L = L2;
+  lv2.out_r_stride = nsmall * stride;
+  lv2.weight_one_based = 0;
+  ReduceBits<F> rb;
+  rb.n = n2;
+  rb.nbits = nbits;
+  rb.nchunks = nchunks;
+  rb.nsmall = nsmall;
+  rb.first_level = first_bit_level;
+  rb.stride = stride;
   ReduceFinal<F> fin;
-  fin.nlevels = nlevels;
-  size_t off_s = 0, off_r = s_entries;
-  const size_t off_t = s_entries + r_entries;
-  for (int l = 0; l < nlevels; l++) {
-    ReduceLevel<F> lv;
-    lv.n_in = lvl_n[l];
-    lv.L = lvl_L[l];
-    lv.weight_one_based = (l == 0) ? 1 : 0;
-    for (int s = 0; s < MAX_SETS; s++) {
-      XYZZ<F>* base = sets.winpart[s];
-      lv.in[s] = (l == 0) ? sets.buckets[s] : base + (off_s - (size_t)nsetsB * lvl_n[l]);
-      lv.out_s[s] = base + off_s;
-      lv.out_r[s] = base + off_r;
-      fin.r[s][l] = base + off_r;
-      fin.wintot[s] = base + off_t;
-    }
-    fin.blocks[l] = lvl_blocks[l];
-    uint32_t lg = 0;
-    while ((1u << lg) < lvl_L[l]) lg++;
-    fin.logL[l] = lg;
-    dim3 rgrid(lvl_blocks[l], nsetsB, (unsigned)nsets);
-    k_reduce_level<F><<<rgrid, lvl_tpb[l], lvl_tpb[l] * sizeof(XYZZ<F>), stream>>>(lv);
+  fin.blocks1 = blocks1;
+  fin.nsmall = nsmall;
+  fin.stride = stride;
+  const uint32_t logL1 = ilog2(L1), logL2 = ilog2(L2);
+  for (uint32_t l = 0; l < REDUCE_MAX_SMALL; l++) {
+    fin.shift[l] = 0;
+    fin.count[l] = 0;
+  }
+  if (L2 > 1) {
+    fin.shift[0] = (uint8_t)logL1;
+    fin.count[0] = (uint16_t)blocks2;
+  }
+  for (uint32_t j = 0; j < nbits; j++) {
+    fin.shift[first_bit_level + j] = (uint8_t)(logL1 + logL2 + j);
+    fin.count[first_bit_level + j] = (uint16_t)nchunks;
+  }
+  for (int s = 0; s < MAX_SETS; s++) {
+    XYZZ<F>* base = sets.winpart[s];
+    lv1.in[s] = sets.buckets[s];
+    lv1.out_s[s] = base;
+    lv1.out_r[s] = base + off_r;
+    lv2.in[s] = base;
+    lv2.out_s[s] = base + off_s2;
+    lv2.out_r[s] = base + off_u;                      // small level 0
+    rb.in[s] = L2 > 1 ? base + off_s2 : base;
+    rb.out[s] = base + off_u;
+    fin.r1[s] = base + off_r;
+    fin.small[s] = base + off_u;
+    fin.wintot[s] = base + off_t;
+  }
+  k_reduce_level<F><<<dim3(blocks1, nsetsB, (unsigned)nsets), tpb1, tpb1 * sizeof(XYZZ<F>), stream>>>(lv1);
+  G16_LAUNCH_CHECK();
+  if (L2 > 1) {
+    k_reduce_level<F><<<dim3(blocks2, nsetsB, (unsigned)nsets), tpb2, tpb2 * sizeof(XYZZ<F>), stream>>>(lv2);
     G16_LAUNCH_CHECK();
-    off_s += (size_t)nsetsB * lvl_n[l + 1];
-    off_r += (size_t)nsetsB * lvl_blocks[l];
   }
-  for (int l = nlevels; l < MSM_MAX_LEVELS; l++) {
-    fin.blocks[l] = 0;
-    fin.logL[l] = 0;
-    for (int s = 0; s < MAX_SETS; s++) fin.r[s][l] = nullptr;
+  if (nbits) {
+    k_reduce_bits<F><<<dim3(nbits * nchunks, nsetsB, (unsigned)nsets), 128, 128 * sizeof(XYZZ<F>), stream>>>(rb);
+    G16_LAUNCH_CHECK();
   }
-  dim3 fgrid2(nsetsB, (unsigned)nsets);
-  k_reduce_final<F><<<fgrid2, 128, 128 * sizeof(XYZZ<F>), stream>>>(fin);
+  k_reduce_final<F><<<dim3(nsetsB, (unsigned)nsets), 128, 128 * sizeof(XYZZ<F>), stream>>>(fin);
   G16_LAUNCH_CHECK();
   AccSets<F> wsets = sets;
   for (int s = 0; s < MAX_SETS; s++) wsets.winpart[s] = sets.winpart[s] + off_t;
