@@ -126,30 +126,46 @@ __global__ void __launch_bounds__(256) k_mask_terms(const SpecPointsDev* spec, c
 // finish later.
 // early (needs only the G1 witness MSMs A1, B1, C1): pi_a, rho, s ** pi_a, r ** rho and
 //   partial_c = s**pi_a + r**rho + (-rs)**delta1 + MSM(zs, C1)
-__global__ void __launch_bounds__(64) k_assemble_early(const MsmResults* res, const MaskTerms* m, g16_proof* proof,
-                                                       G1XYZZ* partial_c) {
-  __shared__ G1XYZZ sh[2];
-  int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) {
-    if (w == 0) {                                     // pi_a, then s ** pi_a       prover.nim:282,298
-      G1XYZZ t;
-      xyzz_add_ni(t, ldv(&m->t_a), ldv(&res->a1));
-      G1Affine pa;
-      xyzz_to_affine_ni(pa, t);
-      stv(reinterpret_cast<G1Affine*>(proof->pi_a), pa);
-      sh[0] = xyzz_scalar_mul(m->s, pa);
-    } else {                                          // rho, then r ** rho         prover.nim:288,299
-      G1XYZZ t;
-      xyzz_add_ni(t, ldv(&m->t_b1), ldv(&res->b1));
-      G1Affine rho;
-      xyzz_to_affine_ni(rho, t);
-      sh[1] = xyzz_scalar_mul(m->r, rho);
+// The two scalar multiplications do not walk a double-and-add chain of ~380 dependent point operations: one
+// thread per half writes the 254 doublings 2^i P into a scratch table, then 128 threads add the entries selected
+// by the scalar's bits in a tree (same scheme as the delta tables of k_mask_terms).  256 threads = 2 halves.
+__global__ void __launch_bounds__(256) k_assemble_early(const MsmResults* res, const MaskTerms* m, g16_proof* proof,
+                                                        G1XYZZ* partial_c, G1XYZZ* scratch) {
+  __shared__ G1XYZZ red[256];
+  const uint32_t h = threadIdx.x >> 7, j = threadIdx.x & 127u;
+  G1XYZZ* tbl = scratch + h * 256;
+  if (j == 0) {
+    G1XYZZ t;
+    if (h == 0) xyzz_add_ni(t, ldv(&m->t_a), ldv(&res->a1));        // pi_a                 prover.nim:282
+    else xyzz_add_ni(t, ldv(&m->t_b1), ldv(&res->b1));              // rho                  prover.nim:288
+    G1Affine pa;
+    xyzz_to_affine_ni(pa, t);
+    if (h == 0) stv(reinterpret_cast<G1Affine*>(proof->pi_a), pa);
+    G1XYZZ p = xyzz_from_affine(pa);
+    for (int i = 0; i < 256; i++) {
+      stv(tbl + i, p);
+      if (i < 255) xyzz_dbl_ni(p, p);
     }
   }
   __syncthreads();
+  const uint32_t* k = h == 0 ? m->s : m->r;                         // s ** pi_a, r ** rho  prover.nim:298,299
+  G1XYZZ acc = xyzz_inf<Fp>();
+  if ((k[j >> 5] >> (j & 31)) & 1u) acc = ldv(tbl + j);
+  const uint32_t j2 = j + 128;
+  if ((k[j2 >> 5] >> (j2 & 31)) & 1u) xyzz_add_ni(acc, acc, ldv(tbl + j2));
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t st = 64; st > 0; st >>= 1) {
+    if (j < st) {
+      G1XYZZ o = red[threadIdx.x + st];
+      xyzz_add_ni(acc, acc, o);
+      red[threadIdx.x] = acc;
+    }
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {                             // + negFr(r*s) ** delta1 + MSM(zs, C1)   prover.nim:300,302
     G1XYZZ t;
-    xyzz_add_ni(t, sh[0], sh[1]);
+    xyzz_add_ni(t, acc, red[128]);
     xyzz_add_ni(t, t, ldv(&m->t_c));
     xyzz_add_ni(t, t, ldv(&res->c1));
     stv(partial_c, t);
@@ -339,7 +355,7 @@ void Prover::init_slot() {
   G16_CUDA(cudaMemset(results_.p, 0, sizeof(MsmResults)));   // all-zero XYZZ == infinity (empty shards)
   mask_.ensure(sizeof(MaskTerms));
   proof_.ensure(sizeof(g16_proof));
-  early_.ensure(sizeof(G1XYZZ));
+  early_.ensure(sizeof(G1XYZZ) * (1 + 512));      // partial pi_c + the two doubling tables of k_assemble_early
   G16_CUDA(cudaMallocHost(reinterpret_cast<void**>(&proof_pinned_), sizeof(g16_proof)));
 }
 
@@ -445,8 +461,8 @@ void Prover::run_msms(g16_stats* stats) {
   if (mask_started_ && R->shard_count == 1) {
     // the MSM-dependent scalar multiplications start now and overlap with the B2 / H work still in flight
     G16_CUDA(cudaStreamWaitEvent(st_[1], ev_[23], 0));
-    k_assemble_early<<<1, 64, 0, st_[1]>>>(results_.as<MsmResults>(), mask_.as<MaskTerms>(), proof_.as<g16_proof>(),
-                                           early_.as<G1XYZZ>());
+    k_assemble_early<<<1, 256, 0, st_[1]>>>(results_.as<MsmResults>(), mask_.as<MaskTerms>(), proof_.as<g16_proof>(),
+                                            early_.as<G1XYZZ>(), early_.as<G1XYZZ>() + 1);
     G16_LAUNCH_CHECK();
     early_done_ = true;
   }
@@ -526,7 +542,8 @@ void Prover::finish_async() {
   G16_CUDA(cudaEventRecord(ev_[19], main_));
   G16_CUDA(cudaStreamWaitEvent(main_, ev_[23], 0));
   if (!early_done_) {                                  // multi-GPU path: the sums arrive only now
-    k_assemble_early<<<1, 64, 0, main_>>>(results_.as<MsmResults>(), m, proof_.as<g16_proof>(), early_.as<G1XYZZ>());
+    k_assemble_early<<<1, 256, 0, main_>>>(results_.as<MsmResults>(), m, proof_.as<g16_proof>(), early_.as<G1XYZZ>(),
+                                           early_.as<G1XYZZ>() + 1);
     G16_LAUNCH_CHECK();
   }
   k_assemble_final<<<1, 64, 0, main_>>>(results_.as<MsmResults>(), m, early_.as<G1XYZZ>(), proof_.as<g16_proof>());
