@@ -517,12 +517,11 @@ void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, i
   const uint32_t nsetsB = g.precomp ? 1u : (uint32_t)g.nwin;
   auto ilog2 = [](uint32_t v) { uint32_t l = 0; while ((1u << l) < v) l++; return l; };
   auto tpb_for = [](uint32_t threads) { return threads < 128u ? (threads < 32u ? 32u : threads) : 128u; };
-  // large bucket sets are throughput-bound: long running sums (2 additions per bucket) and a second level keep
-  // the work minimal; small ones (shards, short MSMs) are latency-bound: short running sums, more bit slicing
-  const bool big = g.nb >= (1u << 18);
-  const uint32_t L1 = big ? 16u : (g.nb >= 4u ? 4u : g.nb);
+  // (shorter running sums with more bit slicing were tried for small bucket sets: less latency per MSM but more
+  // work, and a sharded proof is throughput-bound in aggregate: 1/8 shard 5.27 -> 5.60 ms; not kept)
+  const uint32_t L1 = g.nb >= 16u ? 16u : g.nb;
   const uint32_t n1 = g.nb / L1;
-  const uint32_t L2 = big && n1 >= 8192u ? 8u : 1u;
+  const uint32_t L2 = n1 >= 8192u ? 8u : 1u;                     // level 2 only pays for itself on long arrays
   const uint32_t n2 = n1 / L2;
   const uint32_t tpb1 = tpb_for(n1), blocks1 = (n1 + tpb1 - 1) / tpb1;
   const uint32_t tpb2 = tpb_for(n2), blocks2 = L2 > 1 ? (n2 + tpb2 - 1) / tpb2 : 0;
