@@ -356,7 +356,12 @@ def micro_benchmarks(args, g, lib, zk, w_dev, torch):
     achieved = modmuls * 136.0 / (acc * 1e-3)
     res["roofline"] = {"kernel": "k_bucket_accumulate<Fp> (G1 MSM over the resident window table, XYZZ mixed adds)",
                        "bound": "imad", "achieved": achieved / 1e12, "peak": mac_peak / 1e12, "unit": "TMAC32/s",
-                       "frac": achieved / mac_peak, "traffic": None,
+                       "frac": achieved / mac_peak,
+                       # DRAM bytes per launch of this kernel at 2^20 from the ncu --set full capture
+                       # profiles/r1_v4_ncu_full_bucket_accumulate_g1.csv (1.847 GB read + 0.131 GB written);
+                       # algorithmic gather = pairs x 64 B = 0.87 GB: the kernel is integer-pipe bound, 15 % of HBM
+                       "traffic": 1.979e9 if log_n == 20 else None, "traffic_unit": "bytes per launch (ncu, 2^20)",
+                       "algorithmic_bytes": res["msm_g1"]["pairs"] * 68.0,
                        "peak_source": "measured live: g16_bench_int_pipe(kind=3) x 136 MAC32 per Montgomery multiply "
                                       "(IMAD.WIDE.U32 is half rate; raw mad.lo.u32 rate %.2f T/s)" % (madlo_peak / 1e12),
                        "algorithmic_work": "pairs x 10 modmul x 136 MAC32"}

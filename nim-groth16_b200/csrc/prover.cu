@@ -11,6 +11,7 @@
 // the point range [N*k/G, N*(k+1)/G) of every MSM (msm.nim:107-115): run_msms() then yields partial sums
 // that the host side all-gathers between GPUs.
 #include "prover.cuh"
+#include <stdlib.h>
 #include "ntt.cuh"
 
 namespace g16 {
@@ -342,9 +343,12 @@ void Prover::init_slot() {
   G16_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));      // hi is numerically smaller
   int p_mid = prio_hi + (prio_lo - prio_hi) / 2;
   G16_CUDA(cudaStreamCreateWithPriority(&main_, cudaStreamNonBlocking, prio_hi));
-  G16_CUDA(cudaStreamCreateWithPriority(&st_[0], cudaStreamNonBlocking, prio_lo));    // ABC, quotient, H1
-  G16_CUDA(cudaStreamCreateWithPriority(&st_[1], cudaStreamNonBlocking, p_mid));      // witness sort, A1+B1+C1
-  G16_CUDA(cudaStreamCreateWithPriority(&st_[2], cudaStreamNonBlocking, prio_hi));    // B2
+  int pr[3] = {prio_lo, p_mid, prio_hi};              // ABC+quotient+H1 | witness sort, A1+B1+C1 | B2
+  if (const char* e = getenv("G16_STREAM_PRIO"))      // experiment knob: three letters of l/m/h
+    for (int i = 0; i < 3 && e[i]; i++) pr[i] = e[i] == 'h' ? prio_hi : e[i] == 'm' ? p_mid : prio_lo;
+  G16_CUDA(cudaStreamCreateWithPriority(&st_[0], cudaStreamNonBlocking, pr[0]));
+  G16_CUDA(cudaStreamCreateWithPriority(&st_[1], cudaStreamNonBlocking, pr[1]));
+  G16_CUDA(cudaStreamCreateWithPriority(&st_[2], cudaStreamNonBlocking, pr[2]));
   G16_CUDA(cudaStreamCreateWithPriority(&st_mask_, cudaStreamNonBlocking, prio_hi));
   for (int i = 0; i < 24; i++) G16_CUDA(cudaEventCreate(&ev_[i]));
 
