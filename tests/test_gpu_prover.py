@@ -336,3 +336,52 @@ def test_sharded_prover_async_halves_single_rank(g):
     sp.close()
     assert bytes(raw.pi_c) == want.pi_c.tobytes() and bytes(raw.pi_b) == want.pi_b.tobytes()
     assert np.array_equal(got.pi_a, want.pi_a) and np.array_equal(got.pi_c, want.pi_c)
+
+
+@pytest.mark.parametrize("lg", [20, 22])
+def test_full_size_proofs_pass_the_pairing_verifier(g, lg):
+    """BASELINE.json's full sizes (2^20 headline, 2^22 north-star target): a size-independent property -- the
+    proof of the benchmark workload (bench.make_fixture: chain circuit, GPU fake setup, full-width witness,
+    fixed masks) satisfies the Groth16 verification equation of verifier.nim:31-52 (pairing restatement in the
+    oracle), and the two-shard recombination (msm.nim:107-119) reproduces it byte for byte."""
+    import ctypes as C
+    import bench
+    import bn254_pairing as bp
+    e = E()
+    zk, wit, _ = bench.make_fixture(g, lg)
+    mask = g.Mask(bench.MASK_R, bench.MASK_S)
+    ctx = g.ProverContext(zk)
+    prf = ctx.prove(wit, mask)
+    ctx.close()
+    pub = e.fr_from_std(wit[: zk.npubs + 1])
+    ok = bp.verify_proof(e.g1_from_array(zk.alpha1)[0], e.g2_from_array(zk.beta2)[0], e.g2_from_array(zk.gamma2)[0],
+                         e.g2_from_array(zk.delta2)[0], e.g1_from_array(zk.pointsIC), pub,
+                         e.g1_from_array(prf.pi_a)[0], e.g2_from_array(prf.pi_b)[0], e.g1_from_array(prf.pi_c)[0])
+    assert ok
+    if lg == 20:
+        # a wrong public input must not verify
+        bad = list(pub)
+        bad[1] = (bad[1] + 1) % o.R
+        assert not bp.verify_proof(e.g1_from_array(zk.alpha1)[0], e.g2_from_array(zk.beta2)[0],
+                                   e.g2_from_array(zk.gamma2)[0], e.g2_from_array(zk.delta2)[0],
+                                   e.g1_from_array(zk.pointsIC), bad, e.g1_from_array(prf.pi_a)[0],
+                                   e.g2_from_array(prf.pi_b)[0], e.g1_from_array(prf.pi_c)[0])
+        # the compiled CPU restatement of the reference prover (oracle/g16_oracle_cpu.cpp: its own Montgomery
+        # arithmetic, chunked Pippenger, recursive NTT) on the same 2^20 inputs: bit-identical proof
+        import oracle_cpu as oc
+        pa, pb, pc, _ = oc.prove(zk, wit, bench.MASK_R, bench.MASK_S)
+        assert np.array_equal(pa, prf.pi_a.reshape(-1)) and np.array_equal(pb, prf.pi_b.reshape(-1))
+        assert np.array_equal(pc, prf.pi_c.reshape(-1))
+        import torch
+        w = np.ascontiguousarray(wit)
+        parts = torch.zeros((2, 384), dtype=torch.uint8, device="cuda")
+        for k in range(2):                                   # one shard context at a time: 2 x 2.6 GB of tables
+            c = g.ProverContext(zk, k, 2)
+            c.prove_partials(w.ctypes.data, e.FORM_STD, 0, parts[k].data_ptr())
+            if k == 0:
+                c.close()
+        raw = c.prove_finish(parts.data_ptr(), 2, mask)
+        both = c._proof(raw, w, e.FORM_STD)
+        c.close()
+        assert np.array_equal(both.pi_a, prf.pi_a) and np.array_equal(both.pi_b, prf.pi_b)
+        assert np.array_equal(both.pi_c, prf.pi_c)
