@@ -385,3 +385,29 @@ def test_full_size_proofs_pass_the_pairing_verifier(g, lg):
         c.close()
         assert np.array_equal(both.pi_a, prf.pi_a) and np.array_equal(both.pi_b, prf.pi_b)
         assert np.array_equal(both.pi_c, prf.pi_c)
+
+
+def test_full_size_intermediates_match_cpu_restatement(g):
+    """north_star: "bit-exact agreement with the reference on every intermediate (H coefficients, each MSM result
+    in affine form)" at the headline size 2^20: Az/Bz/Cz, qs and the five MSM results of the GPU entry points
+    (g16_build_abc, g16_quotient, g16_msm_g1/g2) against the compiled CPU restatement on the same inputs."""
+    import bench
+    import oracle_cpu as oc
+    e = E()
+    zk, wit, _ = bench.make_fixture(g, 20)
+    az, bz, cz = g.build_abc(zk, wit)
+    az_c, bz_c, cz_c = oc.build_abc(zk.coeffs, wit, 20)
+    assert np.array_equal(az, az_c) and np.array_equal(bz, bz_c) and np.array_equal(cz, cz_c)
+    qs = g.compute_snarkjs_scalar_coeffs(0, az, bz)                       # prover.nim:158-181
+    assert np.array_equal(qs, oc.quotient(az_c, bz_c, cz_c, 1))
+    w = np.ascontiguousarray(wit)
+    for pts in (zk.pointsA1, zk.pointsB1):                                # prover.nim:282,288
+        assert np.array_equal(g.msm_multi_threaded_g1(0, w, pts, form=e.FORM_STD).reshape(-1), oc.msm_g1(w, pts))
+    assert np.array_equal(g.msm_multi_threaded_g2(0, w, zk.pointsB2, form=e.FORM_STD).reshape(-1),
+                          oc.msm_g2(w, zk.pointsB2))                      # prover.nim:294
+    zs = w[zk.npubs + 1:]                                                 # prover.nim:262-264
+    assert np.array_equal(g.msm_multi_threaded_g1(0, zs, zk.pointsC1, form=e.FORM_STD).reshape(-1),
+                          oc.msm_g1(zs, zk.pointsC1))
+    qs_std = e.fr_std(e.fr_from_mont(qs))
+    assert np.array_equal(g.msm_multi_threaded_g1(0, qs, zk.pointsH1, form=e.FORM_MONT).reshape(-1),
+                          oc.msm_g1(qs_std, zk.pointsH1))                 # prover.nim:301
