@@ -141,7 +141,13 @@ struct NttPassArgs {
   int bitrev_store;     // store element g at dst[bitrev(g)]
 };
 
-constexpr int NTT_THREADS = 256;
+#ifndef G16_NTT_THREADS
+#define G16_NTT_THREADS 256
+#endif
+#ifndef G16_NTT_MINB
+#define G16_NTT_MINB 1
+#endif
+constexpr int NTT_THREADS = G16_NTT_THREADS;
 
 __device__ __forceinline__ Fr ld_fr(const Fr* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -178,7 +184,7 @@ __device__ __forceinline__ void sm_put(uint32_t* sm, uint32_t E, uint32_t p, con
 }
 
 template <bool DIF>
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs a) {
+__global__ void __launch_bounds__(NTT_THREADS, G16_NTT_MINB) k_ntt_pass(NttPassArgs a) {
   extern __shared__ uint32_t sm[];
   const uint32_t E = 1u << (a.k + a.logC);
   const uint32_t tile = blockIdx.x;

@@ -13,7 +13,10 @@
 
 namespace g16 {
 
-constexpr int NTT_TILE_LOG = 11;   // 2048 elements * 32 B = 64 KiB of shared memory per CTA
+#ifndef G16_NTT_TILE_LOG
+#define G16_NTT_TILE_LOG 11
+#endif
+constexpr int NTT_TILE_LOG = G16_NTT_TILE_LOG;   // 2048 elements * 32 B = 64 KiB of shared memory per CTA
 constexpr int NTT_MIN_LOGC = 2;    // strided passes read runs of >= 4 elements = 128 B
 constexpr int NTT_MAX_PASSES = 8;
 

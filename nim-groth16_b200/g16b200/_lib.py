@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libg16b200.so")
+LIB_PATH = os.environ.get("G16B200_LIB") or os.path.join(os.path.dirname(_HERE), "libg16b200.so")
 
 u64p = C.POINTER(C.c_uint64)
 u32p = C.POINTER(C.c_uint32)
