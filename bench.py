@@ -221,7 +221,7 @@ def run_ours(args):
                 last = None
                 for i in range(steps):
                     sp = sps[i % depth]
-                    sp.partials_submit(ptr, mem_kind)
+                    sp.partials_submit(ptr, mem_kind, mask)
                     if i >= depth - 1 and depth > 1:
                         last = sps[(i - (depth - 1)) % depth].complete(mask)
                     elif depth == 1:
@@ -284,7 +284,7 @@ def run_ours(args):
                        "d2h_bytes_per_step": d2h_bytes, "device_ms_per_step": e2e_dev_ms / args.steps,
                        "wall_ms_per_step": e2e_wall_ms / args.steps,
                        "api": "g16_prove_submit/wait (host witness)" if world == 1 else
-                              "g16_prove_partials_submit/wait + all-gather + g16_prove_finish_submit/wait"},
+                              "g16_ctx_set_mask + g16_prove_partials_submit/wait + all-gather + g16_prove_finish_submit/wait"},
                "gpu_launches": int(launches), "clocks": clocks,
                "phase_ms_last_step": {k: round(v, 3) for k, v in stats.items() if k.startswith("ms_")}}
 

@@ -171,6 +171,12 @@ int g16_prove_dev(g16_ctx* ctx, const void* witness_std_dev, const uint64_t r_st
  *   every rank:  g16_prove_partials -> its five partial sums (device buffer of sizeof(g16_partials)),
  *   exchange:    all-gather of those 384-byte records (NCCL / peer copy, done by the host side),
  *   any rank:    g16_prove_finish over the gathered records -> the proof. */
+/* Optional, before g16_prove_partials*: announce the blinding scalars of the proof about to be computed.  The
+ * rank then multiplies its OWN partial sums by them -- s * A_k + r * B1_k (prover.nim:298-299 by linearity), folded
+ * into the c1 field of its record and overlapped with its remaining MSM work -- and g16_prove_finish*, called
+ * with the same r, s, is additions and three affine conversions only.  Every rank of a proof must make the
+ * same choice (all call it, or none). */
+int g16_ctx_set_mask(g16_ctx* ctx, const uint64_t r_std[4], const uint64_t s_std[4]);
 int g16_prove_partials(g16_ctx* ctx, const uint64_t* witness, int witness_form, int witness_mem_kind,
                        void* partials_dev, g16_stats* stats);
 /* asynchronous forms (see g16_prove_submit) */

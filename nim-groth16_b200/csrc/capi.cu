@@ -295,6 +295,13 @@ int g16_prove_wait(g16_ctx* ctx, g16_proof* proof, g16_stats* stats) {
   return guard([&] { prove_wait(ctx, proof, stats); });
 }
 
+int g16_ctx_set_mask(g16_ctx* ctx, const uint64_t r_std[4], const uint64_t s_std[4]) {
+  return guard([&] {
+    G16_REQUIRE(ctx && ctx->prover, "context is null");
+    G16_REQUIRE(!ctx->prover->in_flight(), "a proof is already in flight on this context");
+    ctx->prover->set_mask(r_std, s_std);
+  });
+}
 int g16_prove_partials(g16_ctx* ctx, const uint64_t* witness, int witness_form, int witness_mem_kind,
                        void* partials_dev, g16_stats* stats) {
   return guard([&] {
@@ -342,7 +349,8 @@ int g16_prove_finish(g16_ctx* ctx, const void* gathered_partials_dev, int count,
     G16_REQUIRE(ctx && ctx->prover, "context is null");
     G16_REQUIRE(gathered_partials_dev != nullptr, "partials buffer is null");
     Prover& p = *ctx->prover;
-    p.start_mask(r_std, s_std);
+    if (p.masked_partials()) G16_REQUIRE(p.same_mask(r_std, s_std), "masks differ from g16_ctx_set_mask");
+    else p.start_mask(r_std, s_std);
     p.sum_partials(gathered_partials_dev, count);
     p.finish(proof, nullptr);
   });
@@ -353,7 +361,8 @@ int g16_prove_finish_submit(g16_ctx* ctx, const void* gathered_partials_dev, int
     G16_REQUIRE(ctx && ctx->prover, "context is null");
     G16_REQUIRE(gathered_partials_dev != nullptr, "partials buffer is null");
     Prover& p = *ctx->prover;
-    p.start_mask(r_std, s_std);
+    if (p.masked_partials()) G16_REQUIRE(p.same_mask(r_std, s_std), "masks differ from g16_ctx_set_mask");
+    else p.start_mask(r_std, s_std);
     p.sum_partials(gathered_partials_dev, count);
     p.finish_async();
   });

@@ -15,6 +15,7 @@
 #include <mutex>
 #include "common.cuh"
 #include "field.cuh"
+#include <atomic>
 #include "ntt.cuh"
 #include "ntt_plan.cuh"
 
@@ -230,11 +231,15 @@ __global__ void __launch_bounds__(NTT_THREADS, G16_NTT_MINB) k_ntt_pass(NttPassA
 }
 
 static void launch_pass(bool dif, const NttPassArgs& a, int batch, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // function attributes are per device: a process that switches devices (g16_set_device) needs them on each
+  static std::atomic<uint64_t> attr_devices{0};
+  int dev = 0;
+  G16_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(attr_devices.load(std::memory_order_relaxed) & bit)) {
     G16_CUDA(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     G16_CUDA(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
+    attr_devices.fetch_or(bit, std::memory_order_relaxed);
   }
   size_t E = (size_t)1 << (a.k + a.logC);
   size_t tiles = ((size_t)1 << a.log_n) / E;

@@ -50,18 +50,20 @@ static __device__ void neg_rs(const uint32_t r[8], const uint32_t s[8], uint32_t
 // Tables 2^j * delta1 (G1) and 2^j * delta2 (G2), j < 256, built once per context: the mask terms
 // r ** delta1, s ** delta1, negFr(r*s) ** delta1, s ** delta2 (prover.nim:281,287,293,300) then need no
 // doubling chain -- a block adds the table entries selected by the scalar's bits in a tree.
-__global__ void k_delta_tables(const SpecPointsDev* spec, G1XYZZ* t1, G2XYZZ* t2) {
+__global__ void k_delta_tables(const SpecPointsDev* spec, G1XYZZ* t1, G2XYZZ* t2, G1XYZZ* ta, G1XYZZ* tb) {
   if (threadIdx.x & 31) return;
-  if ((threadIdx.x >> 5) == 0) {
-    G1XYZZ p = xyzz_from_affine(ldv(&spec->delta1));
-    for (int j = 0; j < 256; j++) {
-      stv(t1 + j, p);
-      xyzz_dbl_ni(p, p);
-    }
-  } else {
+  const int w = threadIdx.x >> 5;
+  if (w == 1) {
     G2XYZZ p = xyzz_from_affine(ldv(&spec->delta2));
     for (int j = 0; j < 256; j++) {
       stv(t2 + j, p);
+      xyzz_dbl_ni(p, p);
+    }
+  } else {
+    G1XYZZ p = xyzz_from_affine(ldv(w == 0 ? &spec->delta1 : w == 2 ? &spec->alpha1 : &spec->beta1));
+    G1XYZZ* t = w == 0 ? t1 : w == 2 ? ta : tb;
+    for (int j = 0; j < 256; j++) {
+      stv(t + j, p);
       xyzz_dbl_ni(p, p);
     }
   }
@@ -85,22 +87,23 @@ static __device__ void block_bits_sum(const uint32_t k[8], const XYZZ<F>* table,
   out = acc;
 }
 
-// blocks 0..2: G1 terms; block 3: the G2 term.  256 threads per block.
+// blocks 0..2: G1 terms over the delta1 table; block 3: the G2 term; blocks 4, 5: s ** alpha1 and r ** beta1 (used by
+// the masked-partials finish only).  256 threads per block.
 __global__ void __launch_bounds__(256) k_mask_terms(const SpecPointsDev* spec, const G1XYZZ* t1, const G2XYZZ* t2,
-                                                    MaskTerms* m) {
+                                                    const G1XYZZ* ta, const G1XYZZ* tb, MaskTerms* m) {
   extern __shared__ uint4 red_raw[];
   __shared__ uint32_t k[8];
   const int term = blockIdx.x;
   if (threadIdx.x == 0) {
     if (term == 2) neg_rs(m->r, m->s, k);             // negFr(r*s)                 prover.nim:300
     else
-      for (int i = 0; i < 8; i++) k[i] = (term == 0) ? m->r[i] : m->s[i];
+      for (int i = 0; i < 8; i++) k[i] = (term == 0 || term == 5) ? m->r[i] : m->s[i];
   }
   __syncthreads();
-  if (term < 3) {
+  if (term != 3) {
     G1XYZZ* red = reinterpret_cast<G1XYZZ*>(red_raw);
     G1XYZZ acc;
-    block_bits_sum<Fp>(k, t1, red, acc);
+    block_bits_sum<Fp>(k, term == 4 ? ta : term == 5 ? tb : t1, red, acc);
     if (threadIdx.x == 0) {
       if (term == 0) {                                // alpha1 + r ** delta1       prover.nim:280-281
         xyzz_madd_ni(acc, acc, ldv(&spec->alpha1));
@@ -108,8 +111,12 @@ __global__ void __launch_bounds__(256) k_mask_terms(const SpecPointsDev* spec, c
       } else if (term == 1) {                         // beta1 + s ** delta1        prover.nim:286-287
         xyzz_madd_ni(acc, acc, ldv(&spec->beta1));
         stv(&m->t_b1, acc);
-      } else {
+      } else if (term == 2) {
         stv(&m->t_c, acc);
+      } else if (term == 4) {
+        stv(&m->t_sa, acc);
+      } else {
+        stv(&m->t_rb, acc);
       }
     }
   } else {
@@ -189,6 +196,74 @@ __global__ void __launch_bounds__(64) k_assemble_final(const MsmResults* res, co
     G2Affine pb;
     xyzz_to_affine_ni(pb, t);
     stv(reinterpret_cast<G2Affine*>(proof->pi_b), pb);
+  }
+}
+
+// Masked partials (Prover::set_mask): with pi_a = alpha1 + r delta1 + sum_k A_k and rho = beta1 + s delta1 + sum_k B1_k,
+//   pi_c = sum_k (C_k + s A_k + r B1_k) + sum_k H_k + s alpha1 + r beta1 + (r s) delta1          (prover.nim:298-302)
+// so every shard multiplies ITS OWN partial sums by s and r -- overlapped with its B2 / H work, like the early
+// assembly of the single-GPU path -- and ships c1' = C_k + s A_k + r B1_k; the finish is additions only.
+__global__ void __launch_bounds__(256) k_shard_early(MsmResults* res, const MaskTerms* m, G1XYZZ* scratch) {
+  __shared__ G1XYZZ red[256];
+  const uint32_t h = threadIdx.x >> 7, j = threadIdx.x & 127u;
+  G1XYZZ* tbl = scratch + h * 256;
+  if (j == 0) {
+    G1XYZZ p = ldv(h == 0 ? &res->a1 : &res->b1);
+    for (int i = 0; i < 256; i++) {
+      stv(tbl + i, p);
+      if (i < 255) xyzz_dbl_ni(p, p);
+    }
+  }
+  __syncthreads();
+  const uint32_t* k = h == 0 ? m->s : m->r;
+  G1XYZZ acc = xyzz_inf<Fp>();
+  if ((k[j >> 5] >> (j & 31)) & 1u) acc = ldv(tbl + j);
+  const uint32_t j2 = j + 128;
+  if ((k[j2 >> 5] >> (j2 & 31)) & 1u) xyzz_add_ni(acc, acc, ldv(tbl + j2));
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t st = 64; st > 0; st >>= 1) {
+    if (j < st) {
+      G1XYZZ o = red[threadIdx.x + st];
+      xyzz_add_ni(acc, acc, o);
+      red[threadIdx.x] = acc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    G1XYZZ t;
+    xyzz_add_ni(t, acc, red[128]);
+    xyzz_add_ni(t, t, ldv(&res->c1));
+    stv(&res->c1, t);
+  }
+}
+
+// finish of masked partials: res holds the sums over all shards (c1 = sum of the c1' records)
+__global__ void __launch_bounds__(96) k_assemble_final_masked(const MsmResults* res, const MaskTerms* m,
+                                                              g16_proof* proof) {
+  if (threadIdx.x & 31) return;
+  const int w = threadIdx.x >> 5;
+  if (w == 0) {                                       // pi_a                                    prover.nim:282
+    G1XYZZ t;
+    xyzz_add_ni(t, ldv(&m->t_a), ldv(&res->a1));
+    G1Affine a;
+    xyzz_to_affine_ni(a, t);
+    stv(reinterpret_cast<G1Affine*>(proof->pi_a), a);
+  } else if (w == 1) {                                // pi_b                                    prover.nim:294
+    G2XYZZ t;
+    xyzz_add_ni(t, ldv(&m->t_b2), ldv(&res->b2));
+    G2Affine b;
+    xyzz_to_affine_ni(b, t);
+    stv(reinterpret_cast<G2Affine*>(proof->pi_b), b);
+  } else {                                            // pi_c
+    G1XYZZ t;
+    xyzz_add_ni(t, ldv(&res->c1), ldv(&res->h1));
+    xyzz_add_ni(t, t, ldv(&m->t_sa));
+    xyzz_add_ni(t, t, ldv(&m->t_rb));
+    xyzz_add_ni(t, t, xyzz_neg(ldv(&m->t_c)));        // + (r s) delta1 = -((-r s) delta1)
+    G1Affine c;
+    xyzz_to_affine_ni(c, t);
+    stv(reinterpret_cast<G1Affine*>(proof->pi_c), c);
   }
 }
 
@@ -319,7 +394,10 @@ Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_
                                 (int)(256 * sizeof(G2XYZZ))));
   dtab1.ensure(256 * sizeof(G1XYZZ));
   dtab2.ensure(256 * sizeof(G2XYZZ));
-  k_delta_tables<<<1, 64, 0, main_>>>(spec.as<SpecPointsDev>(), dtab1.as<G1XYZZ>(), dtab2.as<G2XYZZ>());
+  atab1.ensure(256 * sizeof(G1XYZZ));
+  btab1.ensure(256 * sizeof(G1XYZZ));
+  k_delta_tables<<<1, 128, 0, main_>>>(spec.as<SpecPointsDev>(), dtab1.as<G1XYZZ>(), dtab2.as<G2XYZZ>(),
+                                       atab1.as<G1XYZZ>(), btab1.as<G1XYZZ>());
   G16_LAUNCH_CHECK();
   G16_CUDA(cudaStreamSynchronize(main_));
 
@@ -331,7 +409,7 @@ Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_
 
 size_t Resident::bytes() const {
   return tabA1.bytes + tabB1.bytes + tabC1.bytes + tabH1.bytes + tabB2.bytes + csr.ptr.bytes + csr.other.bytes +
-         csr.vals.bytes + dtab1.bytes + dtab2.bytes;
+         csr.vals.bytes + dtab1.bytes + dtab2.bytes + atab1.bytes + btab1.bytes;
 }
 
 void Prover::init_slot() {
@@ -462,7 +540,12 @@ void Prover::run_msms(g16_stats* stats) {
     accW_.run(sortW_, ws, 3, st_[1]);
   }
   G16_CUDA(cudaEventRecord(ev_[7], st_[1]));
-  if (mask_started_ && R->shard_count == 1) {
+  if (masked_partials_) {
+    // this shard's share of s ** pi_a + r ** rho, folded into its c1 partial while B2 / H are still in flight
+    G16_CUDA(cudaStreamWaitEvent(st_[1], ev_[23], 0));
+    k_shard_early<<<1, 256, 0, st_[1]>>>(results_.as<MsmResults>(), mask_.as<MaskTerms>(), early_.as<G1XYZZ>() + 1);
+    G16_LAUNCH_CHECK();
+  } else if (mask_started_ && R->shard_count == 1) {
     // the MSM-dependent scalar multiplications start now and overlap with the B2 / H work still in flight
     G16_CUDA(cudaStreamWaitEvent(st_[1], ev_[23], 0));
     k_assemble_early<<<1, 256, 0, st_[1]>>>(results_.as<MsmResults>(), mask_.as<MaskTerms>(), proof_.as<g16_proof>(),
@@ -531,12 +614,24 @@ void Prover::start_mask(const uint64_t r[4], const uint64_t s[4]) {
   memcpy(rs + 8, s, 32);
   G16_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(m) + offsetof(MaskTerms, r), rs, 64, cudaMemcpyHostToDevice,
                            st_mask_));
-  k_mask_terms<<<4, 256, 256 * sizeof(G2XYZZ), st_mask_>>>(R->spec.as<SpecPointsDev>(), R->dtab1.as<G1XYZZ>(),
-                                                           R->dtab2.as<G2XYZZ>(), m);
+  k_mask_terms<<<6, 256, 256 * sizeof(G2XYZZ), st_mask_>>>(R->spec.as<SpecPointsDev>(), R->dtab1.as<G1XYZZ>(),
+                                                           R->dtab2.as<G2XYZZ>(), R->atab1.as<G1XYZZ>(),
+                                                           R->btab1.as<G1XYZZ>(), m);
   G16_LAUNCH_CHECK();
   G16_CUDA(cudaEventRecord(ev_[23], st_mask_));
   mask_started_ = true;
   early_done_ = false;
+  masked_partials_ = false;
+}
+
+void Prover::set_mask(const uint64_t r[4], const uint64_t s[4]) {
+  start_mask(r, s);
+  memcpy(mask_host_, r, 32);
+  memcpy(mask_host_ + 4, s, 32);
+  masked_partials_ = true;
+}
+bool Prover::same_mask(const uint64_t r[4], const uint64_t s[4]) const {
+  return r && s && memcmp(mask_host_, r, 32) == 0 && memcmp(mask_host_ + 4, s, 32) == 0;
 }
 
 // enqueue the rest of the proof (assembly + 256-byte copy to pinned memory); returns without waiting
@@ -545,6 +640,10 @@ void Prover::finish_async() {
   MaskTerms* m = mask_.as<MaskTerms>();
   G16_CUDA(cudaEventRecord(ev_[19], main_));
   G16_CUDA(cudaStreamWaitEvent(main_, ev_[23], 0));
+  if (masked_partials_) {
+    k_assemble_final_masked<<<1, 96, 0, main_>>>(results_.as<MsmResults>(), m, proof_.as<g16_proof>());
+    G16_LAUNCH_CHECK();
+  } else {
   if (!early_done_) {                                  // multi-GPU path: the sums arrive only now
     k_assemble_early<<<1, 256, 0, main_>>>(results_.as<MsmResults>(), m, proof_.as<g16_proof>(), early_.as<G1XYZZ>(),
                                            early_.as<G1XYZZ>() + 1);
@@ -552,8 +651,10 @@ void Prover::finish_async() {
   }
   k_assemble_final<<<1, 64, 0, main_>>>(results_.as<MsmResults>(), m, early_.as<G1XYZZ>(), proof_.as<g16_proof>());
   G16_LAUNCH_CHECK();
+  }
   mask_started_ = false;
   early_done_ = false;
+  masked_partials_ = false;
   G16_CUDA(cudaMemcpyAsync(proof_pinned_, proof_.p, sizeof(g16_proof), cudaMemcpyDeviceToHost, main_));
   G16_CUDA(cudaEventRecord(ev_[22], main_));
   in_flight_ = true;

@@ -26,6 +26,8 @@ struct alignas(16) MaskTerms {        // prover.nim:279-300, everything that doe
   G1XYZZ t_b1;   // beta1 + s * delta1
   G1XYZZ t_c;    // (-r*s) * delta1
   G2XYZZ t_b2;   // beta2 + s * delta2
+  G1XYZZ t_sa;   // s * alpha1     (masked partials only, see Prover::set_mask)
+  G1XYZZ t_rb;   // r * beta1
   uint32_t r[8], s[8];
 };
 
@@ -47,6 +49,7 @@ struct Resident {
   SparseCsr csr;
   DevBuf spec;                         // SpecPointsDev
   DevBuf dtab1, dtab2;                 // 2^j * delta1 / delta2
+  DevBuf atab1, btab1;                 // 2^j * alpha1 / beta1
   size_t bytes() const;
 };
 
@@ -69,6 +72,11 @@ class Prover {
   bool in_flight() const { return in_flight_; }
   void sum_partials(const void* gathered_dev, int count);   // gathered g16_partials -> results_
   void start_mask(const uint64_t r[4], const uint64_t s[4]);   // mask terms on their own stream
+  // announce the masks BEFORE the partial sums: this shard folds s*A_k + r*B1_k into its c1 partial, so the
+  // finish needs no MSM-dependent scalar multiplication (see k_shard_early)
+  void set_mask(const uint64_t r[4], const uint64_t s[4]);
+  bool masked_partials() const { return masked_partials_; }
+  bool same_mask(const uint64_t r[4], const uint64_t s[4]) const;
   void finish(g16_proof* proof, g16_stats* stats);             // assemble (waits for start_mask)
   int shard_count() const { return R->shard_count; }
   uint32_t nvars() const { return R->nvars; }
@@ -85,7 +93,8 @@ class Prover {
   MsmAccumulator<Fp> accW_, accH_;
   MsmAccumulator<Fp2> accB2_;
   DevBuf witness_, staging_, abc_, qs_, results_, mask_, proof_, early_;
-  bool mask_started_ = false, early_done_ = false, in_flight_ = false;
+  bool mask_started_ = false, early_done_ = false, in_flight_ = false, masked_partials_ = false;
+  uint64_t mask_host_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaStream_t main_ = nullptr, st_mask_ = nullptr, st_[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_[24];
   cudaEvent_t tev_[2] = {nullptr, nullptr};

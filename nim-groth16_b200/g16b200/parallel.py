@@ -1,6 +1,8 @@
 """Multi-GPU proving: one process per GPU (torch.distributed), each owning a contiguous point range of
 every MSM -- the chunking of msm.nim:107-115 lifted from CPU threads to devices.  The only exchange
-is an all-gather of one 384-byte record of partial sums per rank (msm.nim:117-119)."""
+is an all-gather of one 384-byte record of partial sums per rank (msm.nim:117-119).  The blinding scalars are
+announced before the partial sums (g16_ctx_set_mask), so that the two MSM-dependent scalar multiplications of
+prover.nim:298-299 are done per rank on its own partial sums, next to its MSMs, and not after the exchange."""
 from __future__ import annotations
 
 from typing import Optional
@@ -45,6 +47,7 @@ class ShardedProver:
 
     def prove_raw(self, witness_ptr: int, mem_kind: int, mask: Mask, group=None):
         import torch
+        self.ctx.set_mask(mask)              # every rank: its share of s*pi_a + r*rho is computed next to its MSMs
         self.ctx.prove_partials(witness_ptr, FORM_STD, mem_kind, self.partials.data_ptr())
         if self.world > 1:
             allp = gather_partials(self.partials, group)
@@ -54,7 +57,11 @@ class ShardedProver:
         return self.ctx.prove_finish(allp.data_ptr(), self.world, mask)
 
     # asynchronous halves, for overlapping consecutive proofs (one ShardedProver per proof in flight)
-    def partials_submit(self, witness_ptr: int, mem_kind: int):
+    def partials_submit(self, witness_ptr: int, mem_kind: int, mask: Optional[Mask] = None):
+        """`mask`: announce r, s now (g16_ctx_set_mask) -- the same mask must then be given to complete(), and
+        every rank must do the same."""
+        if mask is not None:
+            self.ctx.set_mask(mask)
         _lib.check(_lib.load().g16_prove_partials_submit(self.ctx._h, witness_ptr, FORM_STD, mem_kind,
                                                          self.partials.data_ptr()))
 

@@ -166,6 +166,11 @@ class ProverContext:
         self.last_stats = st.as_dict()
         return raw, self.last_stats
 
+    def set_mask(self, mask: Mask):
+        """g16_ctx_set_mask: announce r, s before the partial sums, so that this rank folds s*A_k + r*B1_k into its
+        record and prove_finish needs no scalar multiplication.  All ranks of a proof call it, or none."""
+        _lib.check(_lib.load().g16_ctx_set_mask(self._h, _limbs4(mask.r), _limbs4(mask.s)))
+
     def prove_partials(self, witness_ptr: int, witness_form: int, mem_kind: int, partials_dev_ptr: int):
         st = _lib.Stats()
         _lib.check(_lib.load().g16_prove_partials(self._h, witness_ptr, witness_form, mem_kind, partials_dev_ptr,

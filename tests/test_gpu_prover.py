@@ -224,16 +224,26 @@ def test_sharded_contexts_recombine_on_one_gpu(g, kat):
     ctx.close()
     w = np.ascontiguousarray(wit)
     for G in (2, 3, 8):
-        parts = torch.zeros((G, 384), dtype=torch.uint8, device="cuda")
         ctxs = [g.ProverContext(zk, k, G) for k in range(G)]
-        for k, c in enumerate(ctxs):
-            c.prove_partials(w.ctypes.data, e.FORM_STD, 0, parts[k].data_ptr())
-        raw = ctxs[0].prove_finish(parts.data_ptr(), G, m)
-        got = ctxs[0]._proof(raw, w, e.FORM_STD)
+        # masked: g16_ctx_set_mask before the partial sums (every shard folds s*A_k + r*B1_k into its c1 record)
+        for masked in (False, True):
+            parts = torch.zeros((G, 384), dtype=torch.uint8, device="cuda")
+            for k, c in enumerate(ctxs):
+                if masked:
+                    c.set_mask(m)
+                c.prove_partials(w.ctypes.data, e.FORM_STD, 0, parts[k].data_ptr())
+            fin = ctxs[G - 1 if masked else 0]
+            raw = fin.prove_finish(parts.data_ptr(), G, m)
+            got = fin._proof(raw, w, e.FORM_STD)
+            assert np.array_equal(got.pi_a, want.pi_a) and np.array_equal(got.pi_b, want.pi_b)
+            assert np.array_equal(got.pi_c, want.pi_c)
+        # the finishing rank must be given the masks it announced
+        ctxs[0].set_mask(m)
+        ctxs[0].prove_partials(w.ctypes.data, e.FORM_STD, 0, parts[0].data_ptr())
+        with pytest.raises(g._lib.G16Error):
+            ctxs[0].prove_finish(parts.data_ptr(), G, g.Mask(m.r + 1, m.s))
         for c in ctxs:
             c.close()
-        assert np.array_equal(got.pi_a, want.pi_a) and np.array_equal(got.pi_b, want.pi_b)
-        assert np.array_equal(got.pi_c, want.pi_c)
 
 
 def test_context_creation_is_stream_ordered_under_dirty_memory(g):
@@ -330,7 +340,7 @@ def test_sharded_prover_async_halves_single_rank(g):
     ctx.close()
     sp = g.parallel.ShardedProver(zk, 0, 1, device=0)
     w = np.ascontiguousarray(wit)
-    sp.partials_submit(w.ctypes.data, 0)
+    sp.partials_submit(w.ctypes.data, 0, m)
     raw = sp.complete(m)
     got = sp.prove(wit, m)
     sp.close()
