@@ -70,6 +70,16 @@ proc g16_ctx_create(zk: ptr G16ZkeyView, shardIndex, shardCount: cint, ctx: ptr 
 proc g16_ctx_destroy(ctx: G16Ctx) {.importc, cdecl.}
 proc g16_prove(ctx: G16Ctx, witness: pointer, witnessForm: cint, r, s: pointer, proof: ptr G16ProofRaw,
                stats: ptr G16Stats): cint {.importc, cdecl.}
+# throughput-oriented hosts: several proofs in flight over one resident key
+proc g16_ctx_clone(ctx: G16Ctx, res: ptr G16Ctx): cint {.importc, cdecl.}
+proc g16_prove_submit(ctx: G16Ctx, witness: pointer, witnessForm, witnessMemKind: cint, r, s: pointer): cint {.importc, cdecl.}
+proc g16_prove_wait(ctx: G16Ctx, proof: ptr G16ProofRaw, stats: ptr G16Stats): cint {.importc, cdecl.}
+# multi-GPU hosts: one context per device over its point range, 384-byte partial records exchanged by the host
+proc g16_ctx_set_mask(ctx: G16Ctx, r, s: pointer): cint {.importc, cdecl.}
+proc g16_prove_partials(ctx: G16Ctx, witness: pointer, witnessForm, witnessMemKind: cint, partialsDev: pointer,
+                        stats: ptr G16Stats): cint {.importc, cdecl.}
+proc g16_prove_finish(ctx: G16Ctx, gatheredPartialsDev: pointer, count: cint, r, s: pointer,
+                      proof: ptr G16ProofRaw): cint {.importc, cdecl.}
 
 # the reference signals every failure with assert()/AssertionDefect (msm.nim:97, prover.nim:224,236,270-276)
 template check(status: cint) =
