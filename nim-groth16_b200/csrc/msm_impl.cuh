@@ -451,6 +451,7 @@ static void launch_accumulate(dim3 grid, cudaStream_t stream, const AccSets<F>& 
     k_bucket_accumulate<F, 1><<<grid, 128, 0, stream>>>(G16_ACC_ARGS);       // 126 registers: 4 CTAs/SM anyway
   } else {
     if (minb == 2) k_bucket_accumulate<F, 2><<<grid, 128, 0, stream>>>(G16_ACC_ARGS);
+    else if (minb == 4) k_bucket_accumulate<F, 4><<<grid, 128, 0, stream>>>(G16_ACC_ARGS);   // 128 registers, heavy spills: 7.8 ms
     else k_bucket_accumulate<F, 3><<<grid, 128, 0, stream>>>(G16_ACC_ARGS);   // 168 registers, a few spills: 6.9 vs 7.3 ms
   }
 #undef G16_ACC_ARGS
