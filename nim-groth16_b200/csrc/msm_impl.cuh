@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include "msm_digits.cuh"
 #include "msm_tree.cuh"
+#include "msm_reduce_plan.cuh"
 
 #ifndef G16_G2_MINB_DEFAULT
 #define G16_G2_MINB_DEFAULT 3
@@ -209,7 +210,6 @@ struct ReduceBits {
   XYZZ<F>* out[MsmAccumulator<F>::MAX_SETS];         // small-level array
   uint32_t n, nbits, nchunks, nsmall, first_level, stride;
 };
-constexpr uint32_t REDUCE_BITS_CHUNK = 1024;
 
 template <class F>
 __global__ void __launch_bounds__(128) k_reduce_bits(ReduceBits<F> a) {
@@ -250,7 +250,6 @@ __global__ void __launch_bounds__(128) k_reduce_bits(ReduceBits<F> a) {
 // grid = (bucket sets, point sets), 128 threads: 48 sum the R1 partials, 4 per small level sum its partials;
 // the doublings of the levels run in parallel, a tree adds the levels.
 constexpr uint32_t REDUCE_FINAL_RTHREADS = 48;
-constexpr uint32_t REDUCE_MAX_SMALL = 20;
 template <class F>
 struct ReduceFinal {
   const XYZZ<F>* r1[MsmAccumulator<F>::MAX_SETS];
@@ -513,25 +512,14 @@ void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, i
   G16_REQUIRE(nsets >= 1 && nsets <= MAX_SETS, "MsmAccumulator: 1..3 point sets");
   const MsmGeometry& g = sorter.geom();
   G16_REQUIRE(g.nwin <= MSM_MAX_WINDOWS, "too many windows");
-  // bucket reduction plan: running sums over 16 consecutive buckets (level 1), over 8 consecutive entries of the
-  // result when it is still long (level 2), then the bit-sliced sum of what is left
+  // bucket reduction plan (msm_reduce_plan.cuh): running sums over 16 consecutive buckets (level 1), over 8
+  // consecutive entries of the result when it is still long (level 2), then the bit-sliced sum of what is left
   const uint32_t nsetsB = g.precomp ? 1u : (uint32_t)g.nwin;
-  auto ilog2 = [](uint32_t v) { uint32_t l = 0; while ((1u << l) < v) l++; return l; };
-  auto tpb_for = [](uint32_t threads) { return threads < 128u ? (threads < 32u ? 32u : threads) : 128u; };
-  // (shorter running sums with more bit slicing were tried for small bucket sets: less latency per MSM but more
-  // work, and a sharded proof is throughput-bound in aggregate: 1/8 shard 5.27 -> 5.60 ms; not kept)
-  const uint32_t L1 = g.nb >= 16u ? 16u : g.nb;
-  const uint32_t n1 = g.nb / L1;
-  const uint32_t L2 = n1 >= 8192u ? 8u : 1u;                     // level 2 only pays for itself on long arrays
-  const uint32_t n2 = n1 / L2;
-  const uint32_t tpb1 = tpb_for(n1), blocks1 = (n1 + tpb1 - 1) / tpb1;
-  const uint32_t tpb2 = tpb_for(n2), blocks2 = L2 > 1 ? (n2 + tpb2 - 1) / tpb2 : 0;
-  const uint32_t nbits = ilog2(n2);
-  const uint32_t nchunks = (n2 + REDUCE_BITS_CHUNK - 1) / REDUCE_BITS_CHUNK;
-  const uint32_t first_bit_level = L2 > 1 ? 1u : 0u;
-  const uint32_t nsmall = first_bit_level + nbits;
-  const uint32_t stride = blocks2 > nchunks ? blocks2 : nchunks;
-  G16_REQUIRE(nsmall <= REDUCE_MAX_SMALL, "too many buckets for the reduction");
+  const ReducePlan rp = msm_reduce_plan(g.nb);
+  G16_REQUIRE(rp.ok, "too many buckets for the reduction");
+  const uint32_t L1 = rp.L1, n1 = rp.n1, L2 = rp.L2, n2 = rp.n2, tpb1 = rp.tpb1, blocks1 = rp.blocks1, tpb2 = rp.tpb2,
+                 blocks2 = rp.blocks2, nbits = rp.nbits, nchunks = rp.nchunks, first_bit_level = rp.first_bit_level,
+                 nsmall = rp.nsmall, stride = rp.stride;
   // scratch per point set: S1 | S2 | R1 partials | small-level partials | one total per bucket set
   const size_t s1_entries = (size_t)nsetsB * n1;
   const size_t s2_entries = L2 > 1 ? (size_t)nsetsB * n2 : 0;
@@ -598,18 +586,9 @@ void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, i
   fin.blocks1 = blocks1;
   fin.nsmall = nsmall;
   fin.stride = stride;
-  const uint32_t logL1 = ilog2(L1), logL2 = ilog2(L2);
   for (uint32_t l = 0; l < REDUCE_MAX_SMALL; l++) {
-    fin.shift[l] = 0;
-    fin.count[l] = 0;
-  }
-  if (L2 > 1) {
-    fin.shift[0] = (uint8_t)logL1;
-    fin.count[0] = (uint16_t)blocks2;
-  }
-  for (uint32_t j = 0; j < nbits; j++) {
-    fin.shift[first_bit_level + j] = (uint8_t)(logL1 + logL2 + j);
-    fin.count[first_bit_level + j] = (uint16_t)nchunks;
+    fin.shift[l] = rp.shift[l];
+    fin.count[l] = rp.count[l];
   }
   for (int s = 0; s < MAX_SETS; s++) {
     XYZZ<F>* base = sets.winpart[s];

@@ -6,6 +6,7 @@
 #include "ec.cuh"
 #include "msm_digits.cuh"
 #include "ntt_plan.cuh"
+#include "msm_reduce_plan.cuh"
 #include <vector>
 using namespace g16;
 
@@ -174,5 +175,73 @@ void he_shift_eval(const uint32_t* in, uint32_t* out, int log_n) {
   emu_dif(v, v, t.tw_inv, log_n, 2, t.coset.data(), false);
   emu_dit(v, t.tw_fwd, log_n);
   memcpy(out, v.data(), n * sizeof(Fr));
+}
+}
+
+// ---- host emulation of the bucket reduction (k_reduce_level x2, k_reduce_bits, k_reduce_final of msm_impl.cuh)
+// driven by the product's own plan (msm_reduce_plan.cuh).  The group is Z / (2^61 - 1): the staging, the partial
+// sum layout and the powers of two are what is checked, not the curve arithmetic.
+static const uint64_t EMU_M = (1ull << 61) - 1;
+static uint64_t emu_add(uint64_t a, uint64_t b) { return (a + b) % EMU_M; }
+static uint64_t emu_dbl_n(uint64_t a, unsigned n) {
+  for (unsigned i = 0; i < n; i++) a = emu_add(a, a);
+  return a;
+}
+extern "C" {
+// returns sum_k (k+1) * v[k] mod 2^61-1 computed through the staged plan; info[0..5] = L1, L2, nbits, nsmall,
+// nchunks, launches
+uint64_t he_reduce_emulate(const uint64_t* v, uint32_t nb, uint32_t* info) {
+  ReducePlan p = msm_reduce_plan(nb);
+  if (!p.ok) return ~0ull;
+  // level 1 (weights j+1), one R partial per block of tpb1 threads
+  std::vector<uint64_t> S1(p.n1), R1(p.blocks1, 0);
+  for (uint32_t t = 0; t < p.n1; t++) {
+    uint64_t running = 0, sum = 0;
+    for (int k = (int)p.L1 - 1; k >= 0; k--) {
+      running = emu_add(running, v[(size_t)t * p.L1 + k] % EMU_M);
+      sum = emu_add(sum, running);
+    }
+    S1[t] = running;
+    R1[t / p.tpb1] = emu_add(R1[t / p.tpb1], sum);
+  }
+  // small-level array [(level) * stride + k]
+  std::vector<uint64_t> small((size_t)p.nsmall * p.stride + 1, 0);
+  std::vector<uint64_t> S2;
+  const std::vector<uint64_t>* S = &S1;
+  if (p.L2 > 1) {                                  // level 2 (weights j), R partials into small level 0
+    S2.resize(p.n2);
+    for (uint32_t t = 0; t < p.n2; t++) {
+      uint64_t running = 0, sum = 0;
+      for (int k = (int)p.L2 - 1; k >= 0; k--) {
+        running = emu_add(running, S1[(size_t)t * p.L2 + k]);
+        if (k > 0) sum = emu_add(sum, running);
+      }
+      S2[t] = running;
+      small[0 * p.stride + t / p.tpb2] = emu_add(small[0 * p.stride + t / p.tpb2], sum);
+    }
+    S = &S2;
+  }
+  for (uint32_t j = 0; j < p.nbits; j++)           // bit slices, one partial per chunk of 1024 entries
+    for (uint32_t c = 0; c < p.nchunks; c++) {
+      uint64_t acc = 0;
+      for (uint32_t i = 0; i < REDUCE_BITS_CHUNK; i++) {
+        uint32_t t = c * REDUCE_BITS_CHUNK + i;
+        if (t < p.n2 && ((t >> j) & 1u)) acc = emu_add(acc, (*S)[t]);
+      }
+      small[(size_t)(p.first_bit_level + j) * p.stride + c] = acc;
+    }
+  // final: R1 + sum over small levels of 2^shift * (sum of count partials)
+  uint64_t total = 0;
+  for (uint32_t k = 0; k < p.blocks1; k++) total = emu_add(total, R1[k]);
+  for (uint32_t l = 0; l < p.nsmall; l++) {
+    uint64_t lv = 0;
+    for (uint32_t k = 0; k < p.count[l]; k++) lv = emu_add(lv, small[(size_t)l * p.stride + k]);
+    total = emu_add(total, emu_dbl_n(lv, p.shift[l]));
+  }
+  if (info) {
+    info[0] = p.L1; info[1] = p.L2; info[2] = p.nbits; info[3] = p.nsmall; info[4] = p.nchunks;
+    info[5] = 1 + (p.L2 > 1 ? 1 : 0) + (p.nbits ? 1 : 0) + 1;
+  }
+  return total;
 }
 }

@@ -168,3 +168,31 @@ def test_shift_eval_domain_emulation(L):
         L.he_shift_eval(buf(data), res, lg)
         got = [o.fr_from_mont_bytes(bytes(res)[32 * i:32 * i + 32]) for i in range(n)]
         assert got == o.shift_eval_domain(xs, D, eta, fast=True), lg
+
+
+def test_bucket_reduction_plan_emulation(L):
+    """msm_reduce_plan.cuh (the plan MsmAccumulator::run executes): running sums, bit-sliced sums and the powers
+    of two of the final assembly give sum_k (k+1) B_k for every bucket-set size the library can pick."""
+    import ctypes as C
+    import numpy as np
+    M = (1 << 61) - 1
+    L.he_reduce_emulate.restype = C.c_uint64
+    rng = np.random.Generator(np.random.PCG64(11))
+    seen_level2 = False
+    for lg in list(range(0, 17)) + [19, 21]:
+        nb = 1 << lg
+        v = rng.integers(0, M, size=nb, dtype=np.uint64)
+        info = (C.c_uint32 * 6)()
+        got = L.he_reduce_emulate(v.ctypes.data_as(C.c_void_p), C.c_uint32(nb), info)
+        k = np.arange(1, nb + 1, dtype=object)
+        want = int(sum(int(a) * int(b) for a, b in zip(k, v.astype(object)))) % M if nb <= 1 << 12 else None
+        if want is None:      # exact big-integer dot product in chunks
+            want = 0
+            vo = v.astype(object)
+            for i in range(0, nb, 1 << 14):
+                want += int(np.dot(np.arange(i + 1, min(nb, i + (1 << 14)) + 1, dtype=object), vo[i:i + (1 << 14)]))
+            want %= M
+        assert got == want, (lg, list(info))
+        assert info[5] <= 4 and info[3] <= 20
+        seen_level2 |= info[1] > 1
+    assert seen_level2                      # the 2^19-bucket sets of the resident prover use level 2
