@@ -171,6 +171,12 @@ int g16_prove_dev(g16_ctx* ctx, const void* witness_std_dev, const uint64_t r_st
  *   every rank:  g16_prove_partials -> its five partial sums (device buffer of sizeof(g16_partials)),
  *   exchange:    all-gather of those 384-byte records (NCCL / peer copy, done by the host side),
  *   any rank:    g16_prove_finish over the gathered records -> the proof. */
+/* The point ranges a context created with (shard_index, shard_count) owns: out = {v_lo, v_hi, h_lo, h_hi}, ranges
+ * of the witness-indexed arrays (A1, B1, C1 shifted by npubs+1, B2) and of the H array.  Contiguous ranges as in
+ * msm.nim:107-111; from four ranks up the H array (and with it buildABC and the quotient) goes to the first ranks only,
+ * which own a smaller share of the witness arrays (environment G16_SHARD_POLICY=uniform: the reference's equal
+ * chunks of every array).  Pure host arithmetic. */
+int g16_shard_ranges(uint64_t nvars, uint64_t domain_size, int shard_index, int shard_count, uint64_t out[4]);
 /* Optional, before g16_prove_partials*: announce the blinding scalars of the proof about to be computed.  The
  * rank then multiplies its OWN partial sums by them -- s * A_k + r * B1_k (prover.nim:298-299 by linearity), folded
  * into the c1 field of its record and overlapped with its remaining MSM work -- and g16_prove_finish*, called

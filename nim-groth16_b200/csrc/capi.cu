@@ -295,6 +295,17 @@ int g16_prove_wait(g16_ctx* ctx, g16_proof* proof, g16_stats* stats) {
   return guard([&] { prove_wait(ctx, proof, stats); });
 }
 
+int g16_shard_ranges(uint64_t nvars, uint64_t domain_size, int shard_index, int shard_count, uint64_t out[4]) {
+  // pure host arithmetic: no device needed, so no guard()
+  if (out == nullptr || shard_count < 1 || shard_index < 0 || shard_index >= shard_count) {
+    set_last_error("g16_shard_ranges: bad argument");
+    return G16_ERR_ARG;
+  }
+  size_t r[4];
+  shard_ranges((size_t)nvars, (size_t)domain_size, shard_index, shard_count, r);
+  for (int i = 0; i < 4; i++) out[i] = r[i];
+  return G16_OK;
+}
 int g16_ctx_set_mask(g16_ctx* ctx, const uint64_t r_std[4], const uint64_t s_std[4]) {
   return guard([&] {
     G16_REQUIRE(ctx && ctx->prover, "context is null");

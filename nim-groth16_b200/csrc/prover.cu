@@ -310,6 +310,42 @@ static void shard_range(size_t N, int k, int G, size_t& lo, size_t& hi) {   // m
   hi = (k == G - 1) ? N : (N * (size_t)(k + 1)) / (size_t)G;
 }
 
+// Point ranges of rank k of G: out = {v_lo, v_hi, h_lo, h_hi} (witness-indexed arrays A1/B1/C1/B2, H array).
+// "uniform" is the reference's chunking of every MSM (msm.nim:107-111).  The default "hgroup" keeps contiguous
+// ranges but gives the H array -- and with it buildABC and the quotient, which cannot be sharded -- to the
+// first m ranks only, and compensates them with a smaller share of the witness arrays: the other ranks skip the
+// quotient altogether and every rank reduces fewer bucket sets.  Shares follow the measured costs at 2^20
+// (witness MSMs 13.0, H MSM 2.05, buildABC + quotient 1.4 ms).  Every rank evaluates the same formula.
+void shard_ranges(size_t nvars, size_t n, int k, int G, size_t out[4]) {
+  static int uniform = -1;
+  if (uniform < 0) {
+    const char* e = getenv("G16_SHARD_POLICY");
+    uniform = (e && e[0] == 'u') ? 1 : 0;
+  }
+  if (G < 4 || uniform) {                      // measured: 13.1 vs 12.9 ms at G = 2, 8.1 vs 8.6 at 4, 5.5 vs 5.9 at 8
+    shard_range(nvars, k, G, out[0], out[1]);
+    shard_range(n, k, G, out[2], out[3]);
+    return;
+  }
+  const int m = G >= 8 ? G / 4 : 1;
+  const double cw = 13.0, ch = 2.05, cq = 1.4;
+  const double d = (cq + ch / m) / cw;
+  double fh = (1.0 - (G - m) * d) / G;
+  if (fh < 0) fh = 0;
+  const double fo = (1.0 - m * fh) / (G - m);
+  auto bound = [&](int idx) -> size_t {
+    if (idx >= G) return nvars;
+    double f = idx <= m ? idx * fh : m * fh + (idx - m) * fo;
+    size_t b = (size_t)(f * (double)nvars + 0.5);
+    return b > nvars ? nvars : b;
+  };
+  out[0] = bound(k);
+  out[1] = bound(k + 1);
+  if (out[1] < out[0]) out[1] = out[0];
+  if (k < m) shard_range(n, k, m, out[2], out[3]);
+  else out[2] = out[3] = n;
+}
+
 // raw points of [lo, hi) -> temporary device buffer.  The copy is issued on the consumer's stream: a plain
 // cudaMemcpy from pageable memory returns once the data is staged and is ordered only against the legacy
 // default stream, which non-blocking streams do not wait for.
@@ -350,8 +386,14 @@ Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_
   cudaStream_t main_ = nullptr;
   G16_CUDA(cudaStreamCreateWithFlags(&main_, cudaStreamNonBlocking));
   // this context's contiguous ranges (msm.nim:107-111): witness-indexed arrays and the H array
-  shard_range(nvars, shard_index, shard_count, v_lo, v_hi);
-  shard_range(n, shard_index, shard_count, h_lo, h_hi);
+  {
+    size_t rg[4];
+    shard_ranges(nvars, n, shard_index, shard_count, rg);
+    v_lo = rg[0];
+    v_hi = rg[1];
+    h_lo = rg[2];
+    h_hi = rg[3];
+  }
   const size_t nv = v_hi - v_lo, nh = h_hi - h_lo;
   if (nv) gw = msm_geometry(nv, msm_pick_window(nv, true), true);
   if (nh) gh = msm_geometry(nh, msm_pick_window(nh, true), true);
@@ -510,9 +552,9 @@ void Prover::run_msms(g16_stats* stats) {
 
   // stream 0: ABC -> quotient -> sort of qs -> MSM over the H table   (prover.nim:245-260, 301)
   G16_CUDA(cudaEventRecord(ev_[1], st_[0]));
-  build_abc(R->csr, w, abc_.as<Fr>(), (int)R->log_n, st_[0]);
+  if (nh) build_abc(R->csr, w, abc_.as<Fr>(), (int)R->log_n, st_[0]);      // ranks without H points skip the chain
   G16_CUDA(cudaEventRecord(ev_[2], st_[0]));
-  quotient(abc_.as<Fr>(), qs_.as<Fr>(), (int)R->log_n, (int)R->flavour, st_[0]);
+  if (nh) quotient(abc_.as<Fr>(), qs_.as<Fr>(), (int)R->log_n, (int)R->flavour, st_[0]);
   G16_CUDA(cudaEventRecord(ev_[3], st_[0]));
   if (nh) {
     sortH_.run(qs_.as<Fr>() + R->h_lo, true, R->gh, st_[0]);

@@ -36,6 +36,9 @@ struct alignas(16) SpecPointsDev {    // SpecPoints (zkey_types.nim:24-31) neede
   G2Affine beta2, delta2;
 };
 
+// {v_lo, v_hi, h_lo, h_hi} of rank k of G (policy: see prover.cu)
+void shard_ranges(size_t nvars, size_t n, int k, int G, size_t out[4]);
+
 // Everything that depends only on the zkey: built once, read-only afterwards, shared by all proofs in flight.
 struct Resident {
   Resident(const g16_zkey_view& zk, int shard_index, int shard_count);

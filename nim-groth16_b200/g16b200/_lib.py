@@ -81,6 +81,7 @@ SIGNATURES = {
     "g16_prove_partials_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "g16_prove_partials_wait": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "g16_prove_finish_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "g16_shard_ranges": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "g16_ctx_set_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "g16_prove_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]),
     "g16_ctx_last_partials": (C.c_int, [C.c_void_p, C.c_void_p]),

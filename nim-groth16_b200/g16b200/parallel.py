@@ -22,6 +22,17 @@ def shard_range(n: int, k: int, g: int):
     return lo, hi
 
 
+def shard_ranges(nvars: int, domain_size: int, k: int, g: int):
+    """g16_shard_ranges: (v_lo, v_hi, h_lo, h_hi) a ProverContext(zkey, k, g) owns -- contiguous ranges of the
+    witness-indexed arrays and of the H array.  From four ranks up the H array (with buildABC and the quotient) goes
+    to the first ranks only, which get a smaller share of the witness arrays; G16_SHARD_POLICY=uniform restores
+    shard_range() for every array."""
+    import ctypes as C
+    out = (C.c_uint64 * 4)()
+    _lib.check(_lib.load().g16_shard_ranges(nvars, domain_size, k, g, out))
+    return tuple(int(x) for x in out)
+
+
 def gather_partials(local: "torch.Tensor", group=None) -> "torch.Tensor":   # noqa: F821
     """All-gather of the per-rank partial-sum records (uint8[384]) -> uint8[world, 384]."""
     import torch

@@ -72,3 +72,26 @@ def test_sharded_partial_sums_recombine_in_the_oracle():
             lo, hi = shard_range(n, k, g)
             acc = o.g1_add(acc, o.msm_naive_g1(ks[lo:hi], pts[lo:hi]))
         assert acc == whole
+
+
+def test_library_shard_ranges_partition_every_array():
+    """g16_shard_ranges (host arithmetic of the C library, no GPU): for every world size the witness ranges and
+    the H ranges are contiguous, ordered, disjoint and cover [0, nvars) / [0, n); the ranks without H points are
+    the ones that skip buildABC and the quotient; world size 1 owns everything."""
+    from g16b200.parallel import shard_ranges
+    for nvars, n in ((1, 2), (5, 8), (1000, 1024), ((1 << 20) - 2 + 2, 1 << 20), ((1 << 22) + 17, 1 << 23)):
+        for g in (1, 2, 3, 4, 5, 8, 16):
+            va = ha = 0
+            h_ranks = 0
+            for k in range(g):
+                v_lo, v_hi, h_lo, h_hi = shard_ranges(nvars, n, k, g)
+                assert v_lo == va and v_hi >= v_lo
+                va = v_hi
+                if h_hi > h_lo:
+                    assert h_lo == ha
+                    ha = h_hi
+                    h_ranks += 1
+                    assert g == 1 or k < max(1, g // 4)     # the H group is among the first ranks
+            assert va == nvars and ha == n and h_ranks >= 1
+            if g == 1:
+                assert shard_ranges(nvars, n, 0, 1) == (0, nvars, 0, n)
