@@ -77,8 +77,8 @@ def test_sharded_partial_sums_recombine_in_the_oracle():
 def test_library_shard_ranges_partition_every_array():
     """g16_shard_ranges (host arithmetic of the C library, no GPU): for every world size the witness ranges and
     the H ranges are contiguous, ordered, disjoint and cover [0, nvars) / [0, n); the ranks without H points are
-    the ones that skip buildABC and the quotient; world size 1 owns everything."""
-    from g16b200.parallel import shard_ranges
+    the ones that skip buildABC and the quotient; below four ranks the split is the reference's chunking."""
+    from g16b200.parallel import shard_range, shard_ranges
     for nvars, n in ((1, 2), (5, 8), (1000, 1024), ((1 << 20) - 2 + 2, 1 << 20), ((1 << 22) + 17, 1 << 23)):
         for g in (1, 2, 3, 4, 5, 8, 16):
             va = ha = 0
@@ -91,7 +91,8 @@ def test_library_shard_ranges_partition_every_array():
                     assert h_lo == ha
                     ha = h_hi
                     h_ranks += 1
-                    assert g == 1 or k < max(1, g // 4)     # the H group is among the first ranks
+                    assert g < 4 or k < max(1, g // 4)      # from 4 ranks up the H group is among the first ranks
             assert va == nvars and ha == n and h_ranks >= 1
-            if g == 1:
-                assert shard_ranges(nvars, n, 0, 1) == (0, nvars, 0, n)
+            if g < 4:
+                for k in range(g):
+                    assert shard_ranges(nvars, n, k, g) == shard_range(nvars, k, g) + shard_range(n, k, g)
