@@ -559,6 +559,39 @@ FpPair fmul2_call(Fp a, Fp b, Fp c, Fp d) {
 #define G16_FP2_MUL(a, b) fmul(a, b)
 #endif
 
+// G16_FP2_WHOLE_CALL: one out-of-line call per Fp2 operation (Karatsuba additions inside the callee) instead of
+// one per Fp product pair: fewer argument moves, which ptxas places on the fma pipe as IMAD.MOV.
+#ifdef G16_FP2_WHOLE_CALL
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+static inline
+#endif
+Fp2 fp2_mul_call(Fp2 a, Fp2 b) {
+  Fp t0, t1;
+  fmul2(a.c0, b.c0, a.c1, b.c1, t0, t1);
+  Fp s = fmul(fadd(a.c0, a.c1), fadd(b.c0, b.c1));
+  Fp2 r;
+  r.c0 = fsub(t0, t1);
+  r.c1 = fsub(fsub(s, t0), t1);
+  return r;
+}
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+static inline
+#endif
+Fp2 fp2_sqr_call(Fp2 a) {
+  Fp t, u;
+  fmul2(a.c0, a.c1, fadd(a.c0, a.c1), fsub(a.c0, a.c1), t, u);
+  Fp2 r;
+  r.c0 = u;
+  r.c1 = fdbl(t);
+  return r;
+}
+G16_HD Fp2 fmul(const Fp2& a, const Fp2& b) { return fp2_mul_call(a, b); }
+G16_HD Fp2 fsqr(const Fp2& a) { return fp2_sqr_call(a); }
+#else
 G16_HD Fp2 fmul(const Fp2& a, const Fp2& b) {  // Karatsuba, 3 Fp mul (two of them interleaved)
 #ifdef G16_FP2_NO_PAIRING
   Fp t0 = G16_FP2_MUL(a.c0, b.c0);
@@ -587,6 +620,7 @@ G16_HD Fp2 fsqr(const Fp2& a) {  // 2 Fp mul, interleaved
   r.c1 = fdbl(t);
   return r;
 }
+#endif
 G16_HD Fp2 finv(const Fp2& a) {
   Fp d = finv(fadd(fsqr(a.c0), fsqr(a.c1)));
   Fp2 r;
