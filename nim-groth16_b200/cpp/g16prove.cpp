@@ -1,0 +1,97 @@
+// g16prove -- the prover half of nim-groth16's command line (cli/cli_main.nim: -p -z -w -o -i -n -t) on top of
+// g16b200.hpp.  Verification, setup and the debug switches stay with the reference's own CLI.
+//
+//   g16prove -z circuit.zkey -w witness.wtns [-o proof.json] [-i public.json] [-n] [-t]
+//            [--mask-r HEX --mask-s HEX]     fixed blinding scalars (testing; default: random, -n: none)
+//            [--info]                        parse the inputs and print their headers only (needs no GPU)
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+#include <string>
+
+#include "g16b200.hpp"
+
+using namespace groth16;
+
+static void printHelp() {
+  printf("usage: g16prove -z <file.zkey> -w <file.wtns> [-o <proof.json>] [-i <public.json>] [-n] [-t]\n"
+         "                [--mask-r <hex> --mask-s <hex>] [--info]\n"
+         " -z, --zkey      the circuit's proving key (snarkjs .zkey, Groth16, bn128)\n"
+         " -w, --wtns      the witness (.wtns)\n"
+         " -o, --output    where to write the proof (default: proof.json)\n"
+         " -i, --io        where to write the public inputs/outputs (default: public.json)\n"
+         " -n, --nomask    no masking (r = s = 0)\n"
+         " -t, --time      print timings\n"
+         "     --info      print the headers of the inputs and exit (no GPU needed)\n");
+}
+
+static Fr parseHexFr(const char* s) {
+  Fr x{};
+  if (s[0] == '0' && (s[1] == 'x' || s[1] == 'X')) s += 2;
+  size_t n = strlen(s);
+  doAssert(n >= 1 && n <= 64, "mask must be 1..64 hex digits");
+  for (size_t i = 0; i < n; i++) {
+    char c = s[n - 1 - i];
+    int d = (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'f') ? c - 'a' + 10 : (c >= 'A' && c <= 'F') ? c - 'A' + 10 : -1;
+    doAssert(d >= 0, "mask is not hexadecimal");
+    x.limb[i / 16] |= (uint64_t)d << (4 * (i % 16));
+  }
+  doAssert(detail::less_than(x.limb, detail::R_MOD), "mask must be below the group order");
+  return x;
+}
+
+int main(int argc, char** argv) {
+  std::string zkey_file, wtns_file, out_file = "proof.json", io_file = "public.json";
+  bool nomask = false, timing = false, info = false, have_r = false, have_s = false;
+  Mask mask;
+  try {
+    for (int i = 1; i < argc; i++) {
+      std::string a = argv[i];
+      auto value = [&]() -> const char* {
+        doAssert(i + 1 < argc, "missing value for an option");
+        return argv[++i];
+      };
+      if (a == "-h" || a == "--help") { printHelp(); return 0; }
+      else if (a == "-z" || a == "--zkey") zkey_file = value();
+      else if (a == "-w" || a == "--wtns" || a == "--witness") wtns_file = value();
+      else if (a == "-o" || a == "--output") out_file = value();
+      else if (a == "-i" || a == "--io" || a == "--input") io_file = value();
+      else if (a == "-n" || a == "--nomask") nomask = true;
+      else if (a == "-t" || a == "--time") timing = true;
+      else if (a == "-p" || a == "--prove") {}                    // the only action of this tool
+      else if (a == "--mask-r") { mask.r = parseHexFr(value()); have_r = true; }
+      else if (a == "--mask-s") { mask.s = parseHexFr(value()); have_s = true; }
+      else if (a == "--info") info = true;
+      else throw AssertionDefect("unknown option `" + a + "`");
+    }
+    if (zkey_file.empty() || wtns_file.empty()) { printHelp(); return 2; }
+    auto t0 = std::chrono::steady_clock::now();
+    ZKey zkey = parseZKey(zkey_file);
+    Witness wtns = parseWitness(wtns_file);
+    auto t1 = std::chrono::steady_clock::now();
+    if (info) {
+      printf("zkey: curve=%s flavour=%s nvars=%d npubs=%d domainSize=%d logDomainSize=%d ncoeffs=%zu\n",
+             zkey.header.curve.c_str(), zkey.header.flavour == Snarkjs ? "Snarkjs" : "JensGroth", zkey.header.nvars,
+             zkey.header.npubs, zkey.header.domainSize, zkey.header.logDomainSize, zkey.ncoeffs);
+      printf("wtns: curve=%s nvars=%d\n", wtns.curve.c_str(), wtns.nvars);
+      return 0;
+    }
+    Proof prf;
+    if (nomask) prf = generateProofWithTrivialMask(0, timing, zkey, wtns);
+    else if (have_r || have_s) prf = generateProofWithMask(0, timing, zkey, wtns, mask);
+    else prf = generateProof(0, timing, zkey, wtns);
+    auto t2 = std::chrono::steady_clock::now();
+    exportProof(out_file, prf);
+    exportPublicIO(io_file, prf);
+    if (timing) {
+      auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+      fprintf(stderr, "parsing the zkey and the witness: %.1f ms; context + proof: %.1f ms\n", ms(t0, t1), ms(t1, t2));
+    }
+    return 0;
+  } catch (const AssertionDefect& e) {
+    fprintf(stderr, "fatal error: %s\n", e.what());
+    return 1;
+  }
+}
