@@ -4,6 +4,8 @@
 //   g16prove -z circuit.zkey -w witness.wtns [-o proof.json] [-i public.json] [-n] [-t]
 //            [--mask-r HEX --mask-s HEX]     fixed blinding scalars (testing; default: random, -n: none)
 //            [--info]                        parse the inputs and print their headers only (needs no GPU)
+//            [-d | --debug]                  print the intermediates of the fine-grained procs (buildABC, the
+//                                            quotient, forward/inverse NTT, the H and pi_B MSMs) as JSON on stdout
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -24,6 +26,7 @@ static void printHelp() {
          " -i, --io        where to write the public inputs/outputs (default: public.json)\n"
          " -n, --nomask    no masking (r = s = 0)\n"
          " -t, --time      print timings\n"
+         " -d, --debug     print the intermediates (Az/Bz/Cz, qs, MSM(qs,H), MSM(w,B2), an NTT round trip) as JSON\n"
          "     --info      print the headers of the inputs and exit (no GPU needed)\n");
 }
 
@@ -44,7 +47,7 @@ static Fr parseHexFr(const char* s) {
 
 int main(int argc, char** argv) {
   std::string zkey_file, wtns_file, out_file = "proof.json", io_file = "public.json";
-  bool nomask = false, timing = false, info = false, have_r = false, have_s = false;
+  bool nomask = false, timing = false, info = false, debug = false, have_r = false, have_s = false;
   Mask mask;
   try {
     for (int i = 1; i < argc; i++) {
@@ -64,6 +67,7 @@ int main(int argc, char** argv) {
       else if (a == "--mask-r") { mask.r = parseHexFr(value()); have_r = true; }
       else if (a == "--mask-s") { mask.s = parseHexFr(value()); have_s = true; }
       else if (a == "--info") info = true;
+      else if (a == "-d" || a == "--debug") debug = true;
       else throw AssertionDefect("unknown option `" + a + "`");
     }
     if (zkey_file.empty() || wtns_file.empty()) { printHelp(); return 2; }
@@ -76,6 +80,40 @@ int main(int argc, char** argv) {
              zkey.header.curve.c_str(), zkey.header.flavour == Snarkjs ? "Snarkjs" : "JensGroth", zkey.header.nvars,
              zkey.header.npubs, zkey.header.domainSize, zkey.header.logDomainSize, zkey.ncoeffs);
       printf("wtns: curve=%s nvars=%d\n", wtns.curve.c_str(), wtns.nvars);
+      return 0;
+    }
+    if (debug) {                                   // the fine-grained procs, one call each (prover.nim:245-301)
+      auto hexFr = [](const Fr& m) {               // Montgomery -> standard -> hex
+        uint64_t v[4];
+        detail::from_mont(m.limb, detail::R_MOD, detail::R_INV, v);
+        char buf[80];
+        snprintf(buf, sizeof buf, "\"0x%016llx%016llx%016llx%016llx\"", (unsigned long long)v[3], (unsigned long long)v[2],
+                 (unsigned long long)v[1], (unsigned long long)v[0]);
+        return std::string(buf);
+      };
+      auto list = [&](const std::vector<Fr>& xs) {
+        std::string s = "[";
+        for (size_t i = 0; i < xs.size(); i++) s += (i ? ", " : "") + hexFr(xs[i]);
+        return s + "]";
+      };
+      ABC abc = buildABC(zkey, wtns.values, (size_t)wtns.nvars);
+      std::vector<Fr> qs = computeSnarkjsScalarCoeffs(0, abc);
+      std::vector<Fr> back = forwardNTT(inverseNTT(abc.valuesAz));
+      bool roundtrip = memcmp(back.data(), abc.valuesAz.data(), back.size() * sizeof(Fr)) == 0;
+      std::vector<G1> hpts(zkey.pointsH1, zkey.pointsH1 + zkey.header.domainSize);
+      G1 msmH = msmMultiThreadedG1(0, qs, hpts);
+      // pi_B's MSM straight through the C entry point: the .wtns values are standard-form integers
+      std::vector<G2> b2(zkey.pointsB2, zkey.pointsB2 + zkey.header.nvars);
+      G2 msmB2;
+      check(g16_msm_g2(reinterpret_cast<const uint64_t*>(wtns.values), G16_FORM_STD,
+                       reinterpret_cast<const uint64_t*>(b2.data()), b2.size(), reinterpret_cast<uint64_t*>(&msmB2)));
+      printf("{ \"Az\": %s,\n  \"Bz\": %s,\n  \"Cz\": %s,\n  \"qs\": %s,\n  \"ntt_roundtrip\": %s,\n",
+             list(abc.valuesAz).c_str(), list(abc.valuesBz).c_str(), list(abc.valuesCz).c_str(), list(qs).c_str(),
+             roundtrip ? "true" : "false");
+      printf("  \"msmH\": [\"%s\", \"%s\"],\n", detail::fp_decimal(msmH.x).c_str(), detail::fp_decimal(msmH.y).c_str());
+      printf("  \"msmB2\": [[\"%s\", \"%s\"], [\"%s\", \"%s\"]] }\n", detail::fp_decimal(msmB2.x.c0).c_str(),
+             detail::fp_decimal(msmB2.x.c1).c_str(), detail::fp_decimal(msmB2.y.c0).c_str(),
+             detail::fp_decimal(msmB2.y.c1).c_str());
       return 0;
     }
     Proof prf;

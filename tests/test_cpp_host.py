@@ -102,3 +102,21 @@ def test_cli_proof_and_json_export_match_the_golden_fixture(exe, files, kat):
     pf.write_witness(str(short), Witness(values=pf.parse_witness(w).values[:-1]))
     r = _run(exe, "-z", z, "-w", str(short), "-n")
     assert r.returncode == 1 and "wrong witness length" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_debug_intermediates_match_the_golden_fixture(exe, files, kat):
+    """The fine-grained procs of g16b200.hpp (buildABC, computeSnarkjsScalarCoeffs, forwardNTT / inverseNTT,
+    msmMultiThreadedG1, g16_msm_g2) called one by one from C++: Az/Bz/Cz, qs and the MSM results of the golden
+    fixture (SURVEY.md Appendix C values)."""
+    z, w, _ = files
+    r = _run(exe, "-z", z, "-w", w, "-d")
+    assert r.returncode == 0, r.stderr
+    got = json.loads(r.stdout)
+    g = kat["snarkjs"]
+    h = lambda v: int(v, 16)
+    for key in ("Az", "Bz", "Cz", "qs"):
+        assert [h(v) for v in got[key]] == [h(v) for v in g[key]], key
+    assert got["ntt_roundtrip"] is True
+    assert [int(v) for v in got["msmH"]] == [h(v) for v in g["fixed"]["msmH"]]
+    assert [[int(a) for a in c] for c in got["msmB2"]] == [[h(a) for a in c] for c in g["fixed"]["msmB2"]]
