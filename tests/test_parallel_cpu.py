@@ -96,3 +96,39 @@ def test_library_shard_ranges_partition_every_array():
             if g < 4:
                 for k in range(g):
                     assert shard_ranges(nvars, n, k, g) == shard_range(nvars, k, g) + shard_range(n, k, g)
+
+
+def test_masked_shard_records_recombine_in_the_oracle(kat):
+    """The algebra of the multi-GPU path (g16_ctx_set_mask, k_shard_early, k_assemble_final_masked of prover.cu)
+    restated with the oracle's group law on the reference's test circuit: every rank ships
+    c1' = C_k + s*A_k + r*B1_k over the ranges of g16_shard_ranges, and
+        pi_c = sum c1'_k + sum H_k + s*alpha1 + r*beta1 + (r s)*delta1,   pi_a, pi_b from the plain sums
+    reproduce generateProofWithMask (prover.nim:278-304) for the uniform split (2 ranks) and the H group (4, 8)."""
+    from g16b200.parallel import shard_ranges
+    zk = o.parse_zkey_bytes(bytes.fromhex(kat["snarkjs"]["zkey_hex"]))
+    w = [int(v, 16) if isinstance(v, str) else int(v) for v in kat["witness"]]
+    r, s = int(kat["mask"]["r"], 16), int(kat["mask"]["s"], 16)
+    inter = {}
+    want = o.generate_proof_with_mask(zk, w, r, s, intermediates=inter)
+    qs = inter["qs"]
+    first = zk.npubs + 1
+    for g in (2, 4, 8):
+        A = B1 = C = H = o.INF_G1
+        B2 = o.INF_G2
+        for k in range(g):
+            v_lo, v_hi, h_lo, h_hi = shard_ranges(zk.nvars, zk.domainSize, k, g)
+            a_k = o.msm_naive_g1(w[v_lo:v_hi], zk.pointsA1[v_lo:v_hi])
+            b1_k = o.msm_naive_g1(w[v_lo:v_hi], zk.pointsB1[v_lo:v_hi])
+            b2_k = o.msm_naive_g2(w[v_lo:v_hi], zk.pointsB2[v_lo:v_hi])
+            c_lo, c_hi = max(v_lo, first), max(v_hi, first)              # C1[j - npubs - 1] multiplies witness[j]
+            c_k = o.msm_naive_g1(w[c_lo:c_hi], zk.pointsC1[c_lo - first:c_hi - first])
+            h_k = o.msm_naive_g1(qs[h_lo:h_hi], zk.pointsH1[h_lo:h_hi])
+            c1p = o.g1_add(o.g1_add(c_k, o.g1_mul(s, a_k)), o.g1_mul(r, b1_k))   # the record's c1 field
+            A, B1, B2 = o.g1_add(A, a_k), o.g1_add(B1, b1_k), o.g2_add(B2, b2_k)
+            C, H = o.g1_add(C, c1p), o.g1_add(H, h_k)
+        pi_a = o.g1_add(o.g1_add(zk.alpha1, o.g1_mul(r, zk.delta1)), A)
+        pi_b = o.g2_add(o.g2_add(zk.beta2, o.g2_mul(s, zk.delta2)), B2)
+        pi_c = o.g1_add(C, H)
+        for term in (o.g1_mul(s, zk.alpha1), o.g1_mul(r, zk.beta1), o.g1_mul(r * s % o.R, zk.delta1)):
+            pi_c = o.g1_add(pi_c, term)
+        assert (pi_a, pi_b, pi_c) == (want.pi_a, want.pi_b, want.pi_c), g
