@@ -41,7 +41,6 @@ static Fr parseHexFr(const char* s) {
     doAssert(d >= 0, "mask is not hexadecimal");
     x.limb[i / 16] |= (uint64_t)d << (4 * (i % 16));
   }
-  doAssert(detail::less_than(x.limb, detail::R_MOD), "mask must be below the group order");
   return x;
 }
 
@@ -64,9 +63,20 @@ int main(int argc, char** argv) {
       else if (a == "-n" || a == "--nomask") nomask = true;
       else if (a == "-t" || a == "--time") timing = true;
       else if (a == "-p" || a == "--prove") {}                    // the only action of this tool
-      else if (a == "--mask-r") { mask.r = parseHexFr(value()); have_r = true; }
-      else if (a == "--mask-s") { mask.s = parseHexFr(value()); have_s = true; }
+      else if (a == "--mask-r" || a == "--mask-s") {
+        Fr x = parseHexFr(value());
+        doAssert(detail::less_than(x.limb, detail::R_MOD), "mask must be below the group order");
+        if (a == "--mask-r") { mask.r = x; have_r = true; }
+        else { mask.s = x; have_s = true; }
+      }
       else if (a == "--info") info = true;
+      else if (a == "--to-decimal") {               // host arithmetic check: Montgomery Fp hex -> decimal string
+        Fr x = parseHexFr(value());
+        Fp m;
+        memcpy(&m, &x, 32);
+        printf("%s\n", detail::fp_decimal(m).c_str());
+        return 0;
+      }
       else if (a == "-d" || a == "--debug") debug = true;
       else throw AssertionDefect("unknown option `" + a + "`");
     }

@@ -61,6 +61,18 @@ def test_cli_error_behaviour(exe, files):
     assert _run(exe, "--help").returncode == 0 and _run(exe).returncode == 2
 
 
+def test_host_montgomery_to_decimal(exe):
+    """detail::from_mont + to_decimal of g16b200.hpp (what exportProof prints) against Python integers."""
+    import random
+    import g16_oracle as o
+    rnd = random.Random(5)
+    vals = [0, 1, o.P - 1, 3] + [rnd.randrange(o.P) for _ in range(20)]
+    for v in vals:
+        mont = v * (1 << 256) % o.P
+        r = _run(exe, "--to-decimal", "%x" % mont)
+        assert r.returncode == 0 and r.stdout.strip() == str(v), (v, r.stdout, r.stderr)
+
+
 @pytest.mark.gpu
 def test_cli_proof_and_json_export_match_the_golden_fixture(exe, files, kat):
     """generateProofWithMask / generateProofWithTrivialMask + exportProof / exportPublicIO through the C++ host:
