@@ -16,10 +16,13 @@ LIB = os.path.join(HERE, "hostemu", "libhostemu.so")
 CSRC = os.path.join(HERE, "..", "nim-groth16_b200", "csrc")
 
 
-@pytest.fixture(scope="module")
-def L():
-    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-I", CSRC, "-o", LIB, SRC])
-    return ctypes.CDLL(LIB)
+# the second build takes the whole-Fp2-call layer the G2 MSM is compiled with (field.cuh, G16_FP2_WHOLE_CALL)
+@pytest.fixture(scope="module", params=["default", "fp2_whole_call"])
+def L(request):
+    lib = LIB if request.param == "default" else LIB.replace(".so", "_whole.so")
+    flags = [] if request.param == "default" else ["-DG16_FP2_WHOLE_CALL"]
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-I", CSRC] + flags + ["-o", lib, SRC])
+    return ctypes.CDLL(lib)
 
 
 def buf(x):
