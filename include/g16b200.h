@@ -43,11 +43,23 @@ extern "C" {
 #define G16_MEM_HOST 0
 #define G16_MEM_DEVICE 1
 
+/* g16_zkey_view.flags */
+#define G16_ZKEY_TRUSTED 1u   /* skip the on-curve validation of the prover points (io.nim:228-236 -> curves.nim:95-107
+                                 mkG1/mkG2 asserts); default: every point is checked on the GPU at g16_ctx_create */
+#define G16_ZKEY_ONE_SHOT 2u  /* the context will serve one or a few proofs (cli_main.nim:193-210): keep the plain points
+                                 instead of building the 13x window tables -- context creation is an upload, the MSMs
+                                 run in the reference-shaped plain layout (about 2x slower per proof) */
+
 const char* g16_last_error(void);
 /* ABI version, device selection (one process per GPU; default device = cudaGetDevice()). */
-int g16_version(void);
+int g16_version(void);               /* 2: g16_zkey_view.flags, 400-byte g16_partials, g16_shard_plan */
 int g16_set_device(int device);
 int g16_device_count(int* count);
+/* Page-locks a caller-owned host range (for example the read-only mmap of a .zkey, files/zkey.nim:196-224) so that
+ * the uploads of g16_ctx_create / the witness copies of g16_prove run as DMA transfers at PCIe speed instead of
+ * staged pageable copies.  Optional; undo with g16_host_unregister before unmapping. */
+int g16_host_register(const void* ptr, size_t bytes);
+int g16_host_unregister(const void* ptr);
 
 /* ------------------------------------------------------------------------------------------------
  * Fine-grained level: one call per reference proc, host buffers in and out.
@@ -93,6 +105,8 @@ typedef struct g16_zkey_view {        /* ZKey (zkey_types.nim:54-60) as raw arra
   uint32_t flavour;                   /* G16_FLAVOUR_* */
   uint32_t coeff_format;              /* G16_COEFF_* */
   uint32_t mem_kind;                  /* G16_MEM_HOST / G16_MEM_DEVICE for the pointers below */
+  uint32_t flags;                     /* G16_ZKEY_* */
+  uint32_t reserved0;
   uint64_t ncoeffs;
   const void* coeffs;                 /* ZKey.coeffs */
   const uint64_t* points_a1;          /* nvars G1            (ProverPoints, zkey_types.nim:34-40) */
@@ -113,7 +127,8 @@ typedef struct g16_proof {            /* Proof (prover.nim:38-43) minus publicIO
   uint64_t pi_c[8];
 } g16_proof;
 
-typedef struct g16_stats {            /* device-side milliseconds (CUDA events on the launch streams) */
+typedef struct g16_stats {            /* device-side milliseconds (CUDA events on the launch streams); for a multi-device
+                                         context the maximum over its devices */
   float ms_h2d;                       /* witness upload */
   float ms_abc;                       /* "building 'ABC'"                    prover.nim:244 */
   float ms_quotient;                  /* "computing the quotient (FFTs)"     prover.nim:249 */
@@ -128,20 +143,34 @@ typedef struct g16_stats {            /* device-side milliseconds (CUDA events o
   uint32_t reserved;
 } g16_stats;
 
-/* partial MSM results of one point-range shard, affine Montgomery: A1, B1, H1, C1 (G1) and B2 (G2) */
+/* partial MSM results of one shard, affine Montgomery: A1, B1, H1, C1 (G1) and B2 (G2); infinity for an MSM the
+ * shard owns no points of.  tag[0] = 1 when the record was produced after g16_ctx_set_mask (msm_c1 then holds
+ * C_k + s*A_k + r*B1_k), tag[1] = a hash of that (r, s): g16_prove_finish refuses a mix of conventions. */
 typedef struct g16_partials {
   uint64_t msm_a1[8];
   uint64_t msm_b1[8];
   uint64_t msm_h1[8];
   uint64_t msm_c1[8];
   uint64_t msm_b2[16];
+  uint64_t tag[2];
 } g16_partials;
 
 typedef struct g16_ctx g16_ctx;
 
-/* Uploads (once) the prover points and the coefficient list of a zkey.  shard_index / shard_count
- * select the contiguous point range [N*k/G, N*(k+1)/G) of every MSM, the chunking of msm.nim:107-115;
- * pass 0, 1 for the whole key on one GPU. */
+/* Uploads (once) the prover points and the coefficient list of a zkey, validates the points (unless
+ * G16_ZKEY_TRUSTED) and builds the resident window tables (unless G16_ZKEY_ONE_SHOT).
+ *   shard_count == 1, shard_index == 0   the whole key on the current device; g16_prove* work on it.  With the
+ *                                        environment variable G16_NGPUS=N (N > 1) this is the next case.
+ *   shard_count == -N (N >= 1)           the whole key spread over N devices of THIS process (devices
+ *                                        shard_index .. shard_index+N-1, or the list in G16_DEVICES="0,1,..."), one
+ *                                        shard each: g16_prove / g16_prove_submit / g16_prove_wait / g16_prove_dev work
+ *                                        unchanged -- witness slices go to each device, the 400-byte partial records
+ *                                        come back by peer copy ordered with events (no host synchronisation), device
+ *                                        shard_index assembles.  This is msm.nim:96-124's internal parallelism
+ *                                        behind the unchanged generateProofWithMask call.
+ *   shard_count == G > 1                 shard shard_index of G on the current device (one process per GPU): use
+ *                                        g16_prove_partials* / g16_prove_finish* and exchange the records yourself.
+ * Which points a shard owns: g16_shard_plan. */
 int g16_ctx_create(const g16_zkey_view* zkey, int shard_index, int shard_count, g16_ctx** out);
 /* Another proof slot over the SAME resident key (tables, CSR rows, spec points are shared and read-only; only
  * the per-proof scratch and streams are new): use it with g16_prove_submit to keep several proofs in flight.
@@ -171,18 +200,23 @@ int g16_prove_dev(g16_ctx* ctx, const void* witness_std_dev, const uint64_t r_st
  *   every rank:  g16_prove_partials -> its five partial sums (device buffer of sizeof(g16_partials)),
  *   exchange:    all-gather of those 384-byte records (NCCL / peer copy, done by the host side),
  *   any rank:    g16_prove_finish over the gathered records -> the proof. */
-/* The point ranges a context created with (shard_index, shard_count) owns: out = {v_lo, v_hi, h_lo, h_hi}, ranges
- * of the witness-indexed arrays (A1, B1, C1 shifted by npubs+1, B2) and of the H array.  Contiguous ranges as in
- * msm.nim:107-111; from four ranks up the H array (and with it buildABC and the quotient) goes to the first ranks only,
- * which own a smaller share of the witness arrays (environment G16_SHARD_POLICY=uniform: the reference's equal
- * chunks of every array).  Pure host arithmetic. */
-int g16_shard_ranges(uint64_t nvars, uint64_t domain_size, int shard_index, int shard_count, uint64_t out[4]);
+/* The point ranges shard shard_index of shard_count owns, out = {a1_lo, a1_hi, b1_lo, b1_hi, c1_lo, c1_hi, b2_lo,
+ * b2_hi, h_lo, h_hi}: a contiguous range (msm.nim:107-111) of each of the five MSMs -- witness indices for A1, B1,
+ * B2 and C1 (C1[j - npubs - 1] multiplies witness[j]), domain indices for H.  Default policy: the MSMs themselves
+ * are placed (whole MSMs, or a tail / head of one, per rank) by a cost model in nvars and the domain size, and
+ * the ranks that own H points are the ones that run buildABC and the quotient.  Environment G16_SHARD_POLICY =
+ * "uniform": the reference's equal chunks of every array; "g2own": the G2 MSM alone on the last shard.
+ * Pure host arithmetic (no device needed); every rank computes the same plan. */
+int g16_shard_plan(uint64_t nvars, uint64_t npubs, uint64_t domain_size, int shard_index, int shard_count,
+                   uint64_t out[10]);
 /* Optional, before g16_prove_partials*: announce the blinding scalars of the proof about to be computed.  The
  * rank then multiplies its OWN partial sums by them -- s * A_k + r * B1_k (prover.nim:298-299 by linearity), folded
  * into the c1 field of its record and overlapped with its remaining MSM work -- and g16_prove_finish*, called
  * with the same r, s, is additions and three affine conversions only.  Every rank of a proof must make the
  * same choice (all call it, or none). */
 int g16_ctx_set_mask(g16_ctx* ctx, const uint64_t r_std[4], const uint64_t s_std[4]);
+/* witness: the full nvars-element array; only the intervals the shard reads are copied (everything on a shard that
+ * owns H points, else the ranges of its MSM pieces). */
 int g16_prove_partials(g16_ctx* ctx, const uint64_t* witness, int witness_form, int witness_mem_kind,
                        void* partials_dev, g16_stats* stats);
 /* asynchronous forms (see g16_prove_submit) */
@@ -191,6 +225,13 @@ int g16_prove_partials_submit(g16_ctx* ctx, const void* witness, int witness_for
 int g16_prove_partials_wait(g16_ctx* ctx, g16_stats* stats);
 int g16_prove_finish_submit(g16_ctx* ctx, const void* gathered_partials_dev, int count, const uint64_t r_std[4],
                             const uint64_t s_std[4]);     /* completed by g16_prove_wait */
+/* Device-side ordering against a caller-owned stream (a cudaStream_t), so that the exchange between the partial sums
+ * and the finish needs no host synchronisation: direction 0 makes `stream` wait for the record of the last
+ * g16_prove_partials_submit; direction 1 makes the context wait for everything enqueued on `stream` so far (the
+ * all-gather) before g16_prove_finish_submit's kernels run. */
+int g16_ctx_order_stream(g16_ctx* ctx, void* stream, int direction);
+/* bytes of witness the last g16_prove* / g16_prove_partials* call copied to this context's device(s) */
+int g16_ctx_last_witness_bytes(g16_ctx* ctx, uint64_t* bytes);
 /* the five MSM sums of the most recent g16_prove* call on this context, as affine records (diagnostics) */
 int g16_ctx_last_partials(g16_ctx* ctx, void* partials_dev);
 int g16_prove_finish(g16_ctx* ctx, const void* gathered_partials_dev, int count, const uint64_t r_std[4],

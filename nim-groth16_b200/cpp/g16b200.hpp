@@ -5,7 +5,7 @@
 // built and exercised (cpp/g16prove.cpp, tests/test_cpp_host.py).
 //
 //   reference (file:line)                                   here
-//   groth16/files/zkey.nim:241-246     parseZKey            groth16::parseZKey      (zero-copy: sections stay in the file buffer)
+//   groth16/files/zkey.nim:241-246     parseZKey            groth16::parseZKey      (zero-copy: the file is mmap'ed, sections are views)
 //   groth16/files/witness.nim:71-76    parseWitness         groth16::parseWitness
 //   groth16/prover.nim:215-304         generateProofWithMask        groth16::generateProofWithMask
 //   groth16/prover.nim:308             generateProofWithTrivialMask groth16::generateProofWithTrivialMask
@@ -22,9 +22,15 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/random.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <array>
 #include <fstream>
-#include <random>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -115,32 +121,70 @@ inline uint64_t rd64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v;
 
 struct Section { const uint8_t* p = nullptr; size_t len = 0; };
 // container.nim:75-93: magic, version, nsections, then (id u32, len u64, payload)*
-inline std::vector<Section> parse_container(const std::vector<uint8_t>& buf, const char magic[4], uint32_t version,
+// A read-only memory mapping of a whole file: the .zkey point sections and the .wtns payload are consumed where
+// the page cache holds them -- no read() into a heap buffer, no per-element parsing.  With
+// pin() the pages are registered with the CUDA driver (g16_host_register), so that the uploads of g16_ctx_create
+// are DMA transfers at PCIe speed instead of staged pageable copies; worth it when the mapping feeds several
+// contexts (one per GPU) or several proofs.
+class FileMap {
+ public:
+  explicit FileMap(const std::string& fname) {
+    fd_ = ::open(fname.c_str(), O_RDONLY);
+    if (fd_ < 0) throw AssertionDefect("cannot open file `" + fname + "`");
+    struct stat st;
+    if (fstat(fd_, &st) != 0) {
+      ::close(fd_);
+      throw AssertionDefect("cannot read file `" + fname + "`");
+    }
+    len_ = (size_t)st.st_size;
+    if (len_) {
+      void* m = mmap(nullptr, len_, PROT_READ, MAP_PRIVATE, fd_, 0);
+      if (m == MAP_FAILED) {
+        ::close(fd_);
+        throw AssertionDefect("cannot map file `" + fname + "`");
+      }
+      p_ = static_cast<const uint8_t*>(m);
+      madvise(const_cast<uint8_t*>(p_), len_, MADV_SEQUENTIAL | MADV_WILLNEED);
+    }
+  }
+  ~FileMap() {
+    if (pinned_) g16_host_unregister(p_);
+    if (p_) munmap(const_cast<uint8_t*>(p_), len_);
+    if (fd_ >= 0) ::close(fd_);
+  }
+  FileMap(const FileMap&) = delete;
+  FileMap& operator=(const FileMap&) = delete;
+  const uint8_t* data() const { return p_; }
+  size_t size() const { return len_; }
+  bool pin() {                         // false when the platform refuses read-only registration: the uploads still work
+    if (!pinned_ && p_) pinned_ = g16_host_register(p_, len_) == 0;
+    return pinned_;
+  }
+
+ private:
+  int fd_ = -1;
+  const uint8_t* p_ = nullptr;
+  size_t len_ = 0;
+  bool pinned_ = false;
+};
+
+inline std::vector<Section> parse_container(const uint8_t* buf, size_t size, const char magic[4], uint32_t version,
                                             int max_id) {
-  doAssert(buf.size() >= 12 && memcmp(buf.data(), magic, 4) == 0, "not a file of the expected kind (bad magic)");
-  doAssert(rd32(buf.data() + 4) == version, "unexpected container version");
-  uint32_t nsec = rd32(buf.data() + 8);
+  doAssert(size >= 12 && memcmp(buf, magic, 4) == 0, "not a file of the expected kind (bad magic)");
+  doAssert(rd32(buf + 4) == version, "unexpected container version");
+  uint32_t nsec = rd32(buf + 8);
   std::vector<Section> out(max_id + 1);
   size_t pos = 12;
   for (uint32_t i = 0; i < nsec; i++) {
-    doAssert(pos + 12 <= buf.size(), "truncated file");
-    uint32_t id = rd32(buf.data() + pos);
-    uint64_t len = rd64(buf.data() + pos + 4);
+    doAssert(pos + 12 <= size, "truncated file");
+    uint32_t id = rd32(buf + pos);
+    uint64_t len = rd64(buf + pos + 4);
     pos += 12;
-    doAssert(pos + len <= buf.size(), "truncated file");
-    if (id <= (uint32_t)max_id) out[id] = Section{buf.data() + pos, (size_t)len};
+    doAssert(len <= size && pos + len <= size, "truncated file");
+    if (id <= (uint32_t)max_id) out[id] = Section{buf + pos, (size_t)len};
     pos += len;
   }
   return out;
-}
-inline std::vector<uint8_t> read_file(const std::string& fname) {
-  std::ifstream f(fname, std::ios::binary | std::ios::ate);
-  if (!f) throw AssertionDefect("cannot open file `" + fname + "`");
-  std::streamsize n = f.tellg();
-  f.seekg(0);
-  std::vector<uint8_t> buf((size_t)n);
-  if (n && !f.read(reinterpret_cast<char*>(buf.data()), n)) throw AssertionDefect("cannot read file `" + fname + "`");
-  return buf;
 }
 }  // namespace detail
 
@@ -164,13 +208,13 @@ struct ZKey {                                    // zkey_types.nim:54-60
   const G1* pointsH1 = nullptr;                  // domainSize
   const uint8_t* coeffs = nullptr;               // ncoeffs packed 44-byte records, value * R^2 (zkey.nim:169-188)
   size_t ncoeffs = 0;
-  std::vector<uint8_t> file;                     // owns the bytes
+  std::shared_ptr<detail::FileMap> file;         // owns the mapping the views point into
 };
 struct Witness {                                 // witness.nim:28-32
   std::string curve = "bn128";
   int nvars = 0;
   const Fr* values = nullptr;                    // standard form, view into `file`
-  std::vector<uint8_t> file;
+  std::shared_ptr<detail::FileMap> file;
 };
 struct Mask { Fr r{}, s{}; };                    // prover.nim:211-213 (standard-form integers)
 struct Proof {                                   // prover.nim:38-43
@@ -182,11 +226,14 @@ struct Proof {                                   // prover.nim:38-43
 };
 
 // ------------------------------------------------------------------------------------------------ files
-inline ZKey parseZKey(const std::string& fname) {                    // zkey.nim:241-246
+// pin: register the mapping with the CUDA driver (FileMap::pin); also taken from the environment G16_PIN_ZKEY=1
+inline ZKey parseZKey(const std::string& fname, bool pin = false) {  // zkey.nim:241-246
   using namespace detail;
   ZKey zk;
-  zk.file = read_file(fname);
-  auto sec = parse_container(zk.file, "zkey", 1, 10);
+  zk.file = std::make_shared<FileMap>(fname);
+  if (const char* e = getenv("G16_PIN_ZKEY")) pin = pin || e[0] == '1';
+  if (pin) zk.file->pin();
+  auto sec = parse_container(zk.file->data(), zk.file->size(), "zkey", 1, 10);
   doAssert(sec[1].len == 4 && rd32(sec[1].p) == 1, "expecting `.zkey` file for a Groth16 prover");   // zkey.nim:110
   const Section& s2 = sec[2];
   doAssert(s2.len == 2 * 4 + 32 + 32 + 3 * 4 + 3 * 64 + 3 * 128, "unexpected section length");      // zkey.nim:122
@@ -228,8 +275,8 @@ inline ZKey parseZKey(const std::string& fname) {                    // zkey.nim
 inline Witness parseWitness(const std::string& fname) {              // witness.nim:71-76
   using namespace detail;
   Witness w;
-  w.file = read_file(fname);
-  auto sec = parse_container(w.file, "wtns", 2, 2);
+  w.file = std::make_shared<FileMap>(fname);
+  auto sec = parse_container(w.file->data(), w.file->size(), "wtns", 2, 2);
   const Section& s1 = sec[1];
   doAssert(s1.len == 4 + 32 + 4, "unexpected section length");                                      // witness.nim:44
   doAssert(rd32(s1.p) == 32, "expecting 256 bit prime");                                            // witness.nim:46
@@ -299,9 +346,13 @@ inline std::vector<Fr> computeQuotientPointwise(int /*nthreads*/, const ABC& abc
 // generateProofWithMask with the zkey kept in HBM between proofs (window tables + CSR rows built once)
 class Prover {
  public:
-  explicit Prover(const ZKey& zkey) : npubs_(zkey.header.npubs), nvars_(zkey.header.nvars) {
+  // flags: G16_ZKEY_* (TRUSTED skips the on-curve checks of io.nim:228-236; ONE_SHOT keeps plain points);
+  // devices = N > 1: the key is spread over N GPUs of this process (also: environment G16_NGPUS)
+  explicit Prover(const ZKey& zkey, uint32_t flags = 0, int devices = 0)
+      : npubs_(zkey.header.npubs), nvars_(zkey.header.nvars) {
     g16_zkey_view v;
     memset(&v, 0, sizeof(v));
+    v.flags = flags;
     v.nvars = (uint32_t)zkey.header.nvars;
     v.npubs = (uint32_t)zkey.header.npubs;
     v.log_domain = (uint32_t)zkey.header.logDomainSize;
@@ -320,7 +371,7 @@ class Prover {
     memcpy(v.beta2, &zkey.specPoints.beta2, 128);
     memcpy(v.delta1, &zkey.specPoints.delta1, 64);
     memcpy(v.delta2, &zkey.specPoints.delta2, 128);
-    check(g16_ctx_create(&v, 0, 1, &ctx_));
+    check(g16_ctx_create(&v, 0, devices > 1 ? -devices : 1, &ctx_));
   }
   ~Prover() { if (ctx_) g16_ctx_destroy(ctx_); }
   Prover(const Prover&) = delete;
@@ -345,11 +396,14 @@ class Prover {
 };
 
 // ------------------------------------------------------------------------------------------------ the reference's prover procs
+// The reference's signature: the zkey arrives with every call (cli_main.nim:193-210), so the context made here
+// serves exactly one proof and is created ONE_SHOT (an upload, no window tables).  A host that proves repeatedly
+// against one key keeps a groth16::Prover instead.
 inline Proof generateProofWithMask(int /*nthreads*/, bool printTimings, const ZKey& zkey, const Witness& wtns,
-                                   const Mask& mask) {                                             // prover.nim:215
+                                   const Mask& mask, int devices = 0) {                            // prover.nim:215
   doAssert(zkey.header.curve == wtns.curve, "zkey.header.curve != wtns.curve");                    // prover.nim:224
   doAssert(zkey.header.nvars == wtns.nvars, "wrong witness length");                               // prover.nim:236
-  Prover prover(zkey);
+  Prover prover(zkey, G16_ZKEY_ONE_SHOT, devices);
   g16_stats st;
   Proof prf = prover.prove(wtns, mask, &st);
   if (printTimings)                                                                                // prover.nim:221
@@ -359,24 +413,31 @@ inline Proof generateProofWithMask(int /*nthreads*/, bool printTimings, const ZK
             st.ms_abc, st.ms_quotient, st.ms_sort_witness, st.ms_msm_g1_witness, st.ms_msm_b2, st.ms_msm_h, st.ms_total);
   return prf;
 }
-inline Proof generateProofWithTrivialMask(int nthreads, bool printTimings, const ZKey& zkey, const Witness& wtns) {
-  return generateProofWithMask(nthreads, printTimings, zkey, wtns, Mask{});                        // prover.nim:308
+inline Proof generateProofWithTrivialMask(int nthreads, bool printTimings, const ZKey& zkey, const Witness& wtns,
+                                          int devices = 0) {
+  return generateProofWithMask(nthreads, printTimings, zkey, wtns, Mask{}, devices);               // prover.nim:308
 }
-inline Fr randFr(std::mt19937_64& gen) {          // rnd.nim: like the reference, NOT a cryptographic source
+// The blinding scalars are what makes the proof zero-knowledge: unlike the reference's std/random (rnd.nim) they are
+// drawn from the kernel CSPRNG (getrandom), 254 bits with rejection sampling, i.e. uniform in [0, r).
+inline Fr randFr() {
   Fr x;
   do {
-    for (int i = 0; i < 4; i++) x.limb[i] = gen();
-    x.limb[3] &= 0x3fffffffffffffffull;           // 254 bits, then rejection
+    size_t got = 0;
+    while (got < sizeof(x.limb)) {
+      ssize_t k = getrandom(reinterpret_cast<char*>(x.limb) + got, sizeof(x.limb) - got, 0);
+      if (k < 0) throw AssertionDefect("getrandom failed");
+      got += (size_t)k;
+    }
+    x.limb[3] &= 0x3fffffffffffffffull;
   } while (!detail::less_than(x.limb, detail::R_MOD));
   return x;
 }
-inline Proof generateProof(int nthreads, bool printTimings, const ZKey& zkey, const Witness& wtns) {   // prover.nim:312-319
-  std::random_device rd;
-  std::mt19937_64 gen(((uint64_t)rd() << 32) ^ rd());
+inline Proof generateProof(int nthreads, bool printTimings, const ZKey& zkey, const Witness& wtns,
+                           int devices = 0) {                                                      // prover.nim:312-319
   Mask m;
-  m.r = randFr(gen);
-  m.s = randFr(gen);
-  return generateProofWithMask(nthreads, printTimings, zkey, wtns, m);
+  m.r = randFr();
+  m.s = randFr();
+  return generateProofWithMask(nthreads, printTimings, zkey, wtns, m, devices);
 }
 
 // ------------------------------------------------------------------------------------------------ export_json.nim:25-80

@@ -3,6 +3,8 @@
 //
 //   g16prove -z circuit.zkey -w witness.wtns [-o proof.json] [-i public.json] [-n] [-t]
 //            [--mask-r HEX --mask-s HEX]     fixed blinding scalars (testing; default: random, -n: none)
+//            [--gpus N]                      spread the key over N GPUs of this process (the library's in-library
+//                                            multi-GPU context; also: environment G16_NGPUS)
 //            [--info]                        parse the inputs and print their headers only (needs no GPU)
 //            [-d | --debug]                  print the intermediates of the fine-grained procs (buildABC, the
 //                                            quotient, forward/inverse NTT, the H and pi_B MSMs) as JSON on stdout
@@ -19,7 +21,7 @@ using namespace groth16;
 
 static void printHelp() {
   printf("usage: g16prove -z <file.zkey> -w <file.wtns> [-o <proof.json>] [-i <public.json>] [-n] [-t]\n"
-         "                [--mask-r <hex> --mask-s <hex>] [--info]\n"
+         "                [--mask-r <hex> --mask-s <hex>] [--gpus <n>] [--info]\n"
          " -z, --zkey      the circuit's proving key (snarkjs .zkey, Groth16, bn128)\n"
          " -w, --wtns      the witness (.wtns)\n"
          " -o, --output    where to write the proof (default: proof.json)\n"
@@ -27,6 +29,7 @@ static void printHelp() {
          " -n, --nomask    no masking (r = s = 0)\n"
          " -t, --time      print timings\n"
          " -d, --debug     print the intermediates (Az/Bz/Cz, qs, MSM(qs,H), MSM(w,B2), an NTT round trip) as JSON\n"
+         "     --gpus      number of GPUs of this box to spread the proof over (default 1)\n"
          "     --info      print the headers of the inputs and exit (no GPU needed)\n");
 }
 
@@ -48,6 +51,7 @@ int main(int argc, char** argv) {
   std::string zkey_file, wtns_file, out_file = "proof.json", io_file = "public.json";
   bool nomask = false, timing = false, info = false, debug = false, have_r = false, have_s = false;
   Mask mask;
+  int gpus = 0;
   try {
     for (int i = 1; i < argc; i++) {
       std::string a = argv[i];
@@ -69,6 +73,7 @@ int main(int argc, char** argv) {
         if (a == "--mask-r") { mask.r = x; have_r = true; }
         else { mask.s = x; have_s = true; }
       }
+      else if (a == "--gpus") gpus = atoi(value());
       else if (a == "--info") info = true;
       else if (a == "--to-decimal") {               // host arithmetic check: Montgomery Fp hex -> decimal string
         Fr x = parseHexFr(value());
@@ -127,9 +132,9 @@ int main(int argc, char** argv) {
       return 0;
     }
     Proof prf;
-    if (nomask) prf = generateProofWithTrivialMask(0, timing, zkey, wtns);
-    else if (have_r || have_s) prf = generateProofWithMask(0, timing, zkey, wtns, mask);
-    else prf = generateProof(0, timing, zkey, wtns);
+    if (nomask) prf = generateProofWithTrivialMask(0, timing, zkey, wtns, gpus);
+    else if (have_r || have_s) prf = generateProofWithMask(0, timing, zkey, wtns, mask, gpus);
+    else prf = generateProof(0, timing, zkey, wtns, gpus);
     auto t2 = std::chrono::steady_clock::now();
     exportProof(out_file, prf);
     exportPublicIO(io_file, prf);

@@ -209,6 +209,29 @@ void fr_from_mont(const Fr* in, Fr* out, size_t n, cudaStream_t stream) {
   k_fr_convert<<<conv_grid(n), 256, 0, stream>>>(in, out, (uint32_t)n, 0);
   G16_LAUNCH_CHECK();
 }
+// standard-form integers that are not below r (a malformed .wtns; io.nim:141-145 fromBig reduces them) are
+// reduced in place; canonical values are only read.  Keeps buildABC (which reduces) and the MSM digits (which
+// assume < 2^254) consistent.
+__global__ void k_fr_reduce_std(Fr* x, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Fr v = ld_fr16(x + i);
+    bool ge = true;                                   // v >= r ?
+#pragma unroll
+    for (int k = 7; k >= 0; k--) {
+      const uint32_t m = FrParams::mod(k);
+      if (v.v[k] != m) {
+        ge = v.v[k] > m;
+        break;
+      }
+    }
+    if (ge) st_fr16(x + i, from_mont(to_mont(v)));
+  }
+}
+void fr_reduce_std(Fr* x, size_t n, cudaStream_t stream) {
+  if (!n) return;
+  k_fr_reduce_std<<<conv_grid(n), 256, 0, stream>>>(x, (uint32_t)n);
+  G16_LAUNCH_CHECK();
+}
 void fr_to_mont(const Fr* in, Fr* out, size_t n, cudaStream_t stream) {
   if (!n) return;
   k_fr_convert<<<conv_grid(n), 256, 0, stream>>>(in, out, (uint32_t)n, 1);

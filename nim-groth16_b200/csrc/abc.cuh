@@ -34,5 +34,7 @@ void build_abc(const SparseCsr& csr, const Fr* witness_std, Fr* abc, int log_n, 
 // elementwise conversions
 void fr_from_mont(const Fr* in, Fr* out, size_t n, cudaStream_t stream);
 void fr_to_mont(const Fr* in, Fr* out, size_t n, cudaStream_t stream);
+// in place: standard-form values >= r are reduced mod r (the reference's fromBig, io.nim:141-145)
+void fr_reduce_std(Fr* x, size_t n, cudaStream_t stream);
 
 }  // namespace g16

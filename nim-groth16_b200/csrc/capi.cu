@@ -13,6 +13,8 @@
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "prover.cuh"
+#include "multi.cuh"
+#include <stdlib.h>
 
 namespace g16 {
 
@@ -129,9 +131,31 @@ static void fixed_base_host(const uint64_t* scalars, size_t n, uint64_t* out) {
 using namespace g16;
 
 struct g16_ctx {
-  std::unique_ptr<Prover> prover;
+  std::unique_ptr<Prover> prover;          // one shard (or the whole key) on one device
+  std::unique_ptr<MultiProver> multi;      // the whole key over several devices of this process
   uint64_t launches0 = 0, launches1 = 0;
 };
+
+// devices of an in-library multi-GPU context: G16_DEVICES="0,1,.." if set, else first .. first+n-1
+static std::vector<int> device_list(int first, int n) {
+  std::vector<int> d;
+  if (const char* e = getenv("G16_DEVICES")) {
+    for (const char* p = e; *p;) {
+      char* end = nullptr;
+      long v = strtol(p, &end, 10);
+      if (end == p) break;
+      d.push_back((int)v);
+      p = (*end == ',') ? end + 1 : end;
+    }
+    if ((int)d.size() >= n) {
+      d.resize((size_t)n);
+      return d;
+    }
+    d.clear();
+  }
+  for (int i = 0; i < n; i++) d.push_back(first + i);
+  return d;
+}
 
 struct g16_msm_plan {
   int g2 = 0;
@@ -147,7 +171,7 @@ struct g16_msm_plan {
 extern "C" {
 
 const char* g16_last_error(void) { return get_last_error(); }
-int g16_version(void) { return 1; }
+int g16_version(void) { return 2; }
 uint64_t g16_kernel_launch_count(void) { return g_launches.load(); }
 
 int g16_set_device(int device) {
@@ -157,6 +181,26 @@ int g16_device_count(int* count) {
   return guard([&] {
     G16_REQUIRE(count != nullptr, "count is null");
     G16_CUDA(cudaGetDeviceCount(count));
+  });
+}
+
+int g16_host_register(const void* ptr, size_t bytes) {
+  return guard([&] {
+    G16_REQUIRE(ptr != nullptr && bytes > 0, "null range");
+    // read-only mappings need the read-only flag; writable ranges take the default
+    cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterReadOnly | cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable);
+    }
+    if (e != cudaSuccess) cudaGetLastError();
+    G16_CUDA(e);
+  });
+}
+int g16_host_unregister(const void* ptr) {
+  return guard([&] {
+    G16_REQUIRE(ptr != nullptr, "null range");
+    G16_CUDA(cudaHostUnregister(const_cast<void*>(ptr)));
   });
 }
 
@@ -239,15 +283,27 @@ int g16_ctx_create(const g16_zkey_view* zkey, int shard_index, int shard_count, 
   return guard([&] {
     G16_REQUIRE(zkey != nullptr && out != nullptr, "null argument");
     std::unique_ptr<g16_ctx> c(new g16_ctx());
-    c->prover.reset(new Prover(*zkey, shard_index, shard_count));
+    int ndev = shard_count < 0 ? -shard_count : 0;
+    if (shard_count == 1 && shard_index == 0)
+      if (const char* e = getenv("G16_NGPUS")) {
+        int v = atoi(e);
+        if (v > 1) ndev = v;
+      }
+    if (ndev >= 1) {
+      G16_REQUIRE(shard_index >= 0, "bad first device");
+      c->multi.reset(new MultiProver(*zkey, device_list(shard_index, ndev)));
+    } else {
+      c->prover.reset(new Prover(*zkey, shard_index, shard_count));
+    }
     *out = c.release();
   });
 }
 int g16_ctx_clone(g16_ctx* ctx, g16_ctx** out) {
   return guard([&] {
-    G16_REQUIRE(ctx && ctx->prover && out, "null argument");
+    G16_REQUIRE(ctx && (ctx->prover || ctx->multi) && out, "null argument");
     std::unique_ptr<g16_ctx> c(new g16_ctx());
-    c->prover.reset(new Prover(ctx->prover->resident()));
+    if (ctx->multi) c->multi.reset(new MultiProver(*ctx->multi));
+    else c->prover.reset(new Prover(ctx->prover->resident()));
     *out = c.release();
   });
 }
@@ -255,10 +311,15 @@ void g16_ctx_destroy(g16_ctx* ctx) { delete ctx; }
 
 static void prove_submit(g16_ctx* ctx, const void* witness, int form, int mem_kind, const uint64_t r[4],
                          const uint64_t s[4]) {
-  G16_REQUIRE(ctx && ctx->prover, "context is null");
+  G16_REQUIRE(ctx && (ctx->prover || ctx->multi), "context is null");
+  ctx->launches0 = g_launches.load();
+  if (ctx->multi) {
+    ctx->multi->submit(witness, form, mem_kind, r, s);
+    ctx->launches1 = g_launches.load();
+    return;
+  }
   G16_REQUIRE(ctx->prover->shard_count() == 1, "g16_prove needs an unsharded context; use g16_prove_partials");
   G16_REQUIRE(!ctx->prover->in_flight(), "a proof is already in flight on this context");
-  ctx->launches0 = g_launches.load();
   Prover& p = *ctx->prover;
   p.start_mask(r, s);
   p.load_witness(witness, form, mem_kind);
@@ -267,9 +328,10 @@ static void prove_submit(g16_ctx* ctx, const void* witness, int form, int mem_ki
   ctx->launches1 = g_launches.load();
 }
 static void prove_wait(g16_ctx* ctx, g16_proof* proof, g16_stats* stats) {
-  G16_REQUIRE(ctx && ctx->prover, "context is null");
+  G16_REQUIRE(ctx && (ctx->prover || ctx->multi), "context is null");
   if (stats) memset(stats, 0, sizeof(*stats));
-  ctx->prover->wait(proof, stats);
+  if (ctx->multi) ctx->multi->wait(proof, stats);
+  else ctx->prover->wait(proof, stats);
   if (stats) stats->kernel_launches = (uint32_t)(ctx->launches1 - ctx->launches0);
 }
 
@@ -295,20 +357,35 @@ int g16_prove_wait(g16_ctx* ctx, g16_proof* proof, g16_stats* stats) {
   return guard([&] { prove_wait(ctx, proof, stats); });
 }
 
-int g16_shard_ranges(uint64_t nvars, uint64_t domain_size, int shard_index, int shard_count, uint64_t out[4]) {
+int g16_shard_plan(uint64_t nvars, uint64_t npubs, uint64_t domain_size, int shard_index, int shard_count,
+                   uint64_t out[10]) {
   // pure host arithmetic: no device needed, so no guard()
   if (out == nullptr || shard_count < 1 || shard_index < 0 || shard_index >= shard_count) {
-    set_last_error("g16_shard_ranges: bad argument");
+    set_last_error("g16_shard_plan: bad argument");
     return G16_ERR_ARG;
   }
-  size_t r[4];
-  shard_ranges((size_t)nvars, (size_t)domain_size, shard_index, shard_count, r);
-  for (int i = 0; i < 4; i++) out[i] = r[i];
+  ShardPlan p;
+  shard_plan((size_t)nvars, (size_t)npubs, (size_t)domain_size, shard_index, shard_count, p);
+  const size_t v[10] = {p.a1_lo, p.a1_hi, p.b1_lo, p.b1_hi, p.c1_lo, p.c1_hi, p.b2_lo, p.b2_hi, p.h_lo, p.h_hi};
+  for (int i = 0; i < 10; i++) out[i] = v[i];
   return G16_OK;
+}
+int g16_ctx_order_stream(g16_ctx* ctx, void* stream, int direction) {
+  return guard([&] {
+    G16_REQUIRE(ctx && ctx->prover, "g16_ctx_order_stream needs a single-shard context");
+    G16_REQUIRE(direction == 0 || direction == 1, "direction must be 0 or 1");
+    ctx->prover->order_stream(reinterpret_cast<cudaStream_t>(stream), direction);
+  });
+}
+int g16_ctx_last_witness_bytes(g16_ctx* ctx, uint64_t* bytes) {
+  return guard([&] {
+    G16_REQUIRE(ctx && (ctx->prover || ctx->multi) && bytes, "null argument");
+    *bytes = ctx->multi ? ctx->multi->last_witness_bytes() : ctx->prover->last_witness_bytes();
+  });
 }
 int g16_ctx_set_mask(g16_ctx* ctx, const uint64_t r_std[4], const uint64_t s_std[4]) {
   return guard([&] {
-    G16_REQUIRE(ctx && ctx->prover, "context is null");
+    G16_REQUIRE(ctx && ctx->prover, "context is null (or a multi-device context, which announces the masks itself)");
     G16_REQUIRE(!ctx->prover->in_flight(), "a proof is already in flight on this context");
     ctx->prover->set_mask(r_std, s_std);
   });
@@ -318,6 +395,7 @@ int g16_prove_partials(g16_ctx* ctx, const uint64_t* witness, int witness_form, 
   return guard([&] {
     G16_REQUIRE(ctx && ctx->prover, "context is null");
     G16_REQUIRE(partials_dev != nullptr, "partials buffer is null");
+    G16_REQUIRE(!ctx->prover->in_flight(), "a proof is already in flight on this context");
     uint64_t l0 = g_launches.load();
     if (stats) memset(stats, 0, sizeof(*stats));
     Prover& p = *ctx->prover;
@@ -333,6 +411,7 @@ int g16_prove_partials_submit(g16_ctx* ctx, const void* witness, int witness_for
   return guard([&] {
     G16_REQUIRE(ctx && ctx->prover, "context is null");
     G16_REQUIRE(partials_dev != nullptr, "partials buffer is null");
+    G16_REQUIRE(!ctx->prover->in_flight(), "a proof is already in flight on this context");
     Prover& p = *ctx->prover;
     p.load_witness(witness, witness_form, witness_mem_kind);
     p.run_msms(nullptr);
@@ -490,14 +569,15 @@ int g16_msm_plan_last_profile(const g16_msm_plan* plan, float* accumulate_ms, fl
 }
 int g16_ctx_timer_start(g16_ctx* ctx) {
   return guard([&] {
-    G16_REQUIRE(ctx && ctx->prover, "context is null");
-    ctx->prover->timer_start();
+    G16_REQUIRE(ctx && (ctx->prover || ctx->multi), "context is null");
+    if (ctx->multi) ctx->multi->timer_start();
+    else ctx->prover->timer_start();
   });
 }
 int g16_ctx_timer_stop(g16_ctx* ctx, float* elapsed_ms) {
   return guard([&] {
-    G16_REQUIRE(ctx && ctx->prover && elapsed_ms, "null argument");
-    *elapsed_ms = ctx->prover->timer_stop();
+    G16_REQUIRE(ctx && (ctx->prover || ctx->multi) && elapsed_ms, "null argument");
+    *elapsed_ms = ctx->multi ? ctx->multi->timer_stop() : ctx->prover->timer_stop();
   });
 }
 

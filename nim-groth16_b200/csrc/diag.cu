@@ -3,7 +3,9 @@
 #include <vector>
 #include "common.cuh"
 #include "ec.cuh"
-#include "field_fp64.cuh"
+#ifdef G16_EXPERIMENTS
+#include "experiments/field_fp64.cuh"   // FP64-pipe multiplier, measured and rejected
+#endif
 
 namespace g16 {
 
@@ -30,7 +32,7 @@ static __host__ __device__ void self_eval(const SelfCase& c, SelfOut& o) {
   o.rinv = finv(c.ra);
   o.pmul = fmul(c.pa, c.pb);
   o.psub = fsub(c.pa, c.pb);
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(G16_EXPERIMENTS)
   o.pdmul = fd_to_fp(dfmul(fd_from_fp(c.pa), fd_from_fp(c.pb)));   // FP64-pipe multiplier: a*b*2^-260
 #else
   {
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(256) k_ip_fmul(Fp* out, uint32_t a) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = fadd(x, z);
 }
 
+#ifdef G16_EXPERIMENTS
 // FP64-pipe experiment: the DFMA Montgomery multiplier of field_fp64.cuh, same dependency pattern as k_ip_fmul
 // mode bit 0: even warps run the IMAD Montgomery multiply loop; bit 1: odd warps run the DFMA primitive loop
 __global__ void __launch_bounds__(256) k_ip_mix(Fp* out, uint32_t a, int mode, int fmul_iters, int dfma_iters,
@@ -276,6 +279,8 @@ __global__ void __launch_bounds__(256) k_ip_mix(Fp* out, uint32_t a, int mode, i
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
+
+#endif
 
 // Instruction-mix probe for a Karatsuba multiplier: per "multiply" 28 rows of 4 wide MACs (112 IMAD.WIDE instead
 // of 128) plus `adds8` carry chains of 8 IADD3 on the ALU pipe; wide = 32 rows and adds8 = 5 models today's fmul.
@@ -338,8 +343,14 @@ void bench_int_pipe(int kind, double* ops_per_sec, float* ms) {
     else if (kind == 10) k_ip_kmix<32, 5><<<blocks, threads>>>(out.as<uint32_t>(), 0x9e3779b9u, 0x7f4a7c15u);
     else if (kind == 11) k_ip_kmix<28, 19><<<blocks, threads>>>(out.as<uint32_t>(), 0x9e3779b9u, 0x7f4a7c15u);
     else if (kind == 12) k_ip_kmix<28, 25><<<blocks, threads>>>(out.as<uint32_t>(), 0x9e3779b9u, 0x7f4a7c15u);
-    else k_ip_mix<<<blocks, threads>>>(out.as<Fp>(), 7, kind == 4 ? 2 : kind == 5 ? 1 : 3, IP_ITERS / 8, IP_ITERS / 8,
-                                      kind <= 6 ? 0xAAu : kind == 7 ? 0xFFu : kind == 8 ? 0x88u : 0xEEu);
+    else {
+#ifdef G16_EXPERIMENTS
+      k_ip_mix<<<blocks, threads>>>(out.as<Fp>(), 7, kind == 4 ? 2 : kind == 5 ? 1 : 3, IP_ITERS / 8, IP_ITERS / 8,
+                                    kind <= 6 ? 0xAAu : kind == 7 ? 0xFFu : kind == 8 ? 0x88u : 0xEEu);
+#else
+      G16_REQUIRE(false, "kinds 4..9 (FP64-pipe experiment) need a library built with `make EXPERIMENTS=1`");
+#endif
+    }
     G16_LAUNCH_CHECK();
   };
   for (int w = 0; w < 2; w++) launch();

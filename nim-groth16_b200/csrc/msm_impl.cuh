@@ -17,7 +17,9 @@
 #include "msm.cuh"
 #include <stdlib.h>
 #include "msm_digits.cuh"
-#include "msm_tree.cuh"
+#ifdef G16_EXPERIMENTS
+#include "experiments/msm_tree.cuh"   // batched-affine accumulation, measured and rejected
+#endif
 #include "msm_reduce_plan.cuh"
 
 #ifndef G16_G2_MINB_DEFAULT
@@ -456,6 +458,7 @@ static void launch_accumulate(dim3 grid, cudaStream_t stream, const AccSets<F>& 
 #undef G16_ACC_ARGS
 }
 
+#ifdef G16_EXPERIMENTS
 // batched-affine bucket accumulation (msm_tree.cuh): tree_log rounds of three launches, then the chunk heads
 // become the bucket sums
 template <class F>
@@ -507,6 +510,8 @@ void MsmAccumulator<F>::run_tree(const MsmSorter& sorter, const MsmPointSet<F>* 
   G16_LAUNCH_CHECK();
 }
 
+#endif
+
 template <class F>
 void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, int nsets, cudaStream_t stream) {
   G16_REQUIRE(nsets >= 1 && nsets <= MAX_SETS, "MsmAccumulator: 1..3 point sets");
@@ -549,8 +554,12 @@ void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, i
     G16_CUDA(cudaEventRecord(pev_[0], stream));
   }
   if (g.tree_log) {
+#ifdef G16_EXPERIMENTS
     run_tree(sorter, in, nsets, sets.buckets, stream);
     if (profile) G16_CUDA(cudaEventRecord(pev_[1], stream));
+#else
+    G16_REQUIRE(false, "batched-affine tree mode needs a library built with `make EXPERIMENTS=1`");
+#endif
   } else {
     dim3 agrid(div_up(g.max_items, 128), (unsigned)nsets);
     launch_accumulate<F>(agrid, stream, sets, sorter, g);

@@ -43,9 +43,13 @@ int msm_pick_window(size_t n, bool precomp) {
 static int default_tree_log() {
   static int v = -1;
   if (v < 0) {
+#ifdef G16_EXPERIMENTS
     const char* e = getenv("G16_MSM_TREE");
     v = e ? atoi(e) : G16_MSM_TREE_DEFAULT;
     if (v != 0 && (v < 3 || v > MSM_TREE_MAX_LOG)) v = 0;
+#else
+    v = 0;                                           // the tree mode is not compiled into the default library
+#endif
   }
   return v;
 }
@@ -171,6 +175,7 @@ __global__ void k_make_items(const uint32_t* __restrict__ start, const uint32_t*
   }
 }
 
+#ifdef G16_EXPERIMENTS
 // Lists of the additions of every tree round (msm_tree.cuh): slot j with chunk-relative position q is a left
 // operand of round r when q is a multiple of 2^(r+1) and q + 2^r is still inside the chunk.  Round 0 also lists
 // the last element of odd-length chunks (bit 31: no partner) so that it is copied into the working array.
@@ -254,6 +259,8 @@ __global__ void __launch_bounds__(TREE_LIST_TPB) k_tree_lists(const uint32_t* __
   }
 }
 
+#endif
+
 MsmSorter::~MsmSorter() {}
 
 size_t MsmSorter::workspace_bytes() const {
@@ -334,6 +341,7 @@ void MsmSorter::run(const Fr* scalars, bool scalars_mont, const MsmGeometry& g, 
                                              (int64_t)g.max_items, 0, item_bits, stream));
     return;
   }
+#ifdef G16_EXPERIMENTS
   // batched-affine tree: per-round addition lists
   size_t total = 0;
   for (int r = 0; r < MSM_TREE_MAX_LOG; r++) {
@@ -350,6 +358,9 @@ void MsmSorter::run(const Fr* scalars, bool scalars_mont, const MsmGeometry& g, 
       keys_[1].as<uint32_t>(), start_.as<uint32_t>(), (uint32_t)m, g.nbuckets, g.tree_log,
       tree_list_.as<uint32_t>(), offs, tree_cnt_.as<uint32_t>());
   G16_LAUNCH_CHECK();
+#else
+  G16_REQUIRE(false, "batched-affine tree mode needs a library built with `make EXPERIMENTS=1`");
+#endif
 }
 
 }  // namespace g16

@@ -1,0 +1,140 @@
+// In-library multi-GPU prover (see multi.cuh).  Replaces the thread-pool parallelism inside
+// generateProofWithMask (groth16/prover.nim:215-304 with groth16/bn128/msm.nim:96-124) by devices of one process.
+#include "multi.cuh"
+#include <string.h>
+
+namespace g16 {
+
+MultiProver::MultiProver(const g16_zkey_view& zk, const std::vector<int>& devices) : dev_(devices) {
+  const int G = (int)dev_.size();
+  G16_REQUIRE(G >= 1, "multi-device context needs at least one device");
+  int have = 0;
+  G16_CUDA(cudaGetDeviceCount(&have));
+  for (int d : dev_) G16_REQUIRE(d >= 0 && d < have, "multi-device context: no such device");
+  // NVLink peer access between the assembling device and the others (the witness may also live on any of them)
+  for (int k = 1; k < G; k++) {
+    if (dev_[k] == dev_[0]) continue;               // the same device listed twice: a test configuration
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, dev_[0], dev_[k]);
+    if (!can) continue;                             // peer copies are then staged through the host by the runtime
+    {
+      DeviceGuard g(dev_[0]);
+      cudaError_t e = cudaDeviceEnablePeerAccess(dev_[k], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) G16_CUDA(e);
+      cudaGetLastError();
+    }
+    {
+      DeviceGuard g(dev_[k]);
+      cudaError_t e = cudaDeviceEnablePeerAccess(dev_[0], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) G16_CUDA(e);
+      cudaGetLastError();
+    }
+  }
+  for (int k = 0; k < G; k++) {
+    DeviceGuard g(dev_[k]);
+    shard_.emplace_back(new Prover(zk, k, G));
+  }
+  init_slot();
+}
+
+MultiProver::MultiProver(const MultiProver& base) : dev_(base.dev_) {
+  for (size_t k = 0; k < dev_.size(); k++) {
+    DeviceGuard g(dev_[k]);
+    shard_.emplace_back(new Prover(base.shard_[k]->resident()));
+  }
+  init_slot();
+}
+
+void MultiProver::init_slot() {
+  const int G = (int)dev_.size();
+  for (int k = 0; k < G; k++) {
+    DeviceGuard g(dev_[k]);
+    local_.emplace_back(new DevBuf());
+    local_.back()->ensure(sizeof(PartialsAffine));
+    cudaEvent_t e = nullptr;
+    G16_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    sent_.push_back(e);
+  }
+  DeviceGuard g(dev_[0]);
+  gathered_.ensure((size_t)G * sizeof(PartialsAffine));
+}
+
+MultiProver::~MultiProver() {
+  for (size_t k = 0; k < shard_.size(); k++) {
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(dev_[k]);
+    shard_[k].reset();                    // ~Prover synchronises its device
+    local_[k].reset();
+    if (sent_[k]) cudaEventDestroy(sent_[k]);
+    cudaSetDevice(prev);
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(dev_[0]);
+  gathered_.release();
+  cudaSetDevice(prev);
+}
+
+void MultiProver::submit(const void* witness, int form, int mem_kind, const uint64_t r[4], const uint64_t s[4]) {
+  const int G = (int)dev_.size();
+  G16_REQUIRE(!in_flight(), "a proof is already in flight on this context");
+  PartialsAffine* all = gathered_.as<PartialsAffine>();
+  // the device with the G2 work (the longest single kernel) is the last of the plan: enqueue it first
+  for (int i = 0; i < G; i++) {
+    const int k = G - 1 - i;
+    DeviceGuard g(dev_[k]);
+    Prover& p = *shard_[k];
+    p.set_mask(r, s);                     // every shard folds s*A_k + r*B1_k into its record next to its MSMs
+    p.load_witness(witness, form, mem_kind);
+    p.run_msms(nullptr);
+    p.partials_to_affine_async(local_[k]->p);
+    G16_CUDA(cudaMemcpyPeerAsync(all + k, dev_[0], local_[k]->p, dev_[k], sizeof(PartialsAffine), p.main_stream()));
+    G16_CUDA(cudaEventRecord(sent_[k], p.main_stream()));
+  }
+  DeviceGuard g(dev_[0]);
+  Prover& head = *shard_[0];
+  for (int k = 1; k < G; k++) G16_CUDA(cudaStreamWaitEvent(head.main_stream(), sent_[k], 0));
+  head.sum_partials(all, G);
+  head.finish_async();
+}
+
+void MultiProver::wait(g16_proof* proof, g16_stats* stats) {
+  {
+    DeviceGuard g(dev_[0]);
+    shard_[0]->wait(proof, stats);
+  }
+  if (!stats) return;
+  // the head waited for every record, so the other shards' events have completed: maximum per phase
+  for (size_t k = 1; k < shard_.size(); k++) {
+    g16_stats st;
+    memset(&st, 0, sizeof(st));
+    DeviceGuard g(dev_[k]);
+    shard_[k]->collect_stats(&st);
+    float* a = &stats->ms_h2d;
+    const float* b = &st.ms_h2d;
+    for (int i = 0; i < 8; i++)           // ms_h2d .. reserved_ms
+      if (b[i] > a[i]) a[i] = b[i];
+  }
+}
+
+size_t MultiProver::last_witness_bytes() const {
+  size_t t = 0;
+  for (auto& p : shard_) t += p->last_witness_bytes();
+  return t;
+}
+size_t MultiProver::resident_bytes() const {
+  size_t t = 0;
+  for (auto& p : shard_) t += p->resident_bytes();
+  return t;
+}
+void MultiProver::timer_start() {
+  DeviceGuard g(dev_[0]);
+  shard_[0]->timer_start();
+}
+float MultiProver::timer_stop() {
+  DeviceGuard g(dev_[0]);
+  return shard_[0]->timer_stop();
+}
+
+}  // namespace g16

@@ -12,6 +12,8 @@
 // that the host side all-gathers between GPUs.
 #include "prover.cuh"
 #include <stdlib.h>
+#include <string.h>
+#include <algorithm>
 #include "ntt.cuh"
 
 namespace g16 {
@@ -268,7 +270,12 @@ __global__ void __launch_bounds__(96) k_assemble_final_masked(const MsmResults* 
 }
 
 // XYZZ results -> affine partial sums (the per-chunk prj.affine of msm.nim:54,81)
-__global__ void __launch_bounds__(160) k_partials_to_affine(const MsmResults* res, PartialsAffine* out) {
+__global__ void __launch_bounds__(160) k_partials_to_affine(const MsmResults* res, PartialsAffine* out, uint64_t masked,
+                                                            uint64_t mask_hash) {
+  if (threadIdx.x == 1) {
+    out->tag[0] = masked;
+    out->tag[1] = mask_hash;
+  }
   if (threadIdx.x & 31) return;
   int w = threadIdx.x >> 5;
   if (w < 4) {
@@ -285,7 +292,16 @@ __global__ void __launch_bounds__(160) k_partials_to_affine(const MsmResults* re
 }
 
 // gathered affine partial sums -> XYZZ totals (res += sync pending[k], msm.nim:117-119)
-__global__ void __launch_bounds__(160) k_sum_partials(const PartialsAffine* parts, int count, MsmResults* res) {
+// The records must agree with the finishing context on the mask convention (all masked with this (r, s), or none):
+// a mix would give a wrong pi_c, so it is reported through the status word instead.
+__global__ void __launch_bounds__(160) k_sum_partials(const PartialsAffine* parts, int count, MsmResults* res,
+                                                      uint64_t masked, uint64_t mask_hash, uint32_t* status) {
+  if (threadIdx.x == 1) {
+    uint32_t bad = 0;
+    for (int i = 0; i < count; i++)
+      if (parts[i].tag[0] != masked || parts[i].tag[1] != mask_hash) bad = 1;
+    *status = bad;
+  }
   if (threadIdx.x & 31) return;
   int w = threadIdx.x >> 5;
   if (w < 4) {
@@ -305,71 +321,239 @@ __global__ void __launch_bounds__(160) k_sum_partials(const PartialsAffine* part
 }
 
 // ---------------------------------------------------------------------------------------
+// Shard plan: which points of which MSM a rank owns.
+//
+// The reference chunks every MSM alike, [N*k/G, N*(k+1)/G) per thread (msm.nim:107-111).  Across GPUs that makes
+// every rank run all five MSMs on a G-times smaller input: five bucket-set reductions, five latency-bound tails and
+// a smaller window (more pairs per point) on every rank -- the fixed costs that capped 8-GPU efficiency at 0.55.
+// The default policy "line" therefore places the MSMs themselves: the work of one proof is laid
+// on a line  [H | A1 | B1 | C1 | B2]  weighted by a cost model, and rank k owns the k-th segment, i.e. whole MSMs
+// plus at most a tail of one array and a head of another.  buildABC and the quotient cannot be split by points, so
+// every rank that owns H points computes them; the number m of such ranks is the one that minimises the modelled
+// load of the slowest rank.  Environment G16_SHARD_POLICY: "line" (default), "uniform" (the reference's equal
+// chunks of every array), "g2own" (BASELINE.json configs[3]: the G2 MSM alone on the last rank, the rest as "line").
+// Every rank evaluates the same arithmetic, so the plan needs no communication.
+// ---------------------------------------------------------------------------------------
 static void shard_range(size_t N, int k, int G, size_t& lo, size_t& hi) {   // msm.nim:107-111
   lo = (N * (size_t)k) / (size_t)G;
   hi = (k == G - 1) ? N : (N * (size_t)(k + 1)) / (size_t)G;
 }
 
-// Point ranges of rank k of G: out = {v_lo, v_hi, h_lo, h_hi} (witness-indexed arrays A1/B1/C1/B2, H array).
-// "uniform" is the reference's chunking of every MSM (msm.nim:107-111).  The default "hgroup" keeps contiguous
-// ranges but gives the H array -- and with it buildABC and the quotient, which cannot be sharded -- to the
-// first m ranks only, and compensates them with a smaller share of the witness arrays: the other ranks skip the
-// quotient altogether and every rank reduces fewer bucket sets.  Shares follow the measured costs at 2^20
-// (witness MSMs 13.0, H MSM 2.05, buildABC + quotient 1.4 ms).  Every rank evaluates the same formula.
-void shard_ranges(size_t nvars, size_t n, int k, int G, size_t out[4]) {
-  static int uniform = -1;
-  if (uniform < 0) {
+// Cost model in units of one 254-bit Montgomery multiplication at the measured peak rate (6.76e10 /s on a B200 --
+// only ratios matter).  Efficiencies are the measured fractions of that peak: G1 accumulate 0.95, G2
+// 0.82, bucket reduction 0.8, NTT passes 0.7; a sorted pair costs 2.2 (CUB radix sort, HBM-bound).
+static double msm_cost(size_t npts, bool g2) {
+  if (!npts) return 0.0;
+  const int c = msm_pick_window(npts, true);
+  const double W = (double)msm_num_windows(c), nb = (double)((size_t)1 << (c - 1));
+  const double acc = (double)npts * W * (g2 ? 28.0 / 0.82 : 10.0 / 0.95);
+  const double red = nb * (g2 ? 85.0 : 30.0) / 0.8;
+  const double sort = (double)npts * W * 2.2 * (g2 ? 0.25 : 1.0);       // B2 shares the witness sort when co-located
+  const double tail = 4.0e6 * (g2 ? 2.8 : 1.0);                         // reduce / combine tails not hidden by overlap
+  return acc + red + sort + tail;
+}
+static double quotient_cost(size_t n, size_t nvars) {
+  const double lg = (double)ceil_log2_sz(n);
+  const double ntt = 3.0 * ((double)n * lg + (double)n) + 2.0 * (double)n;   // 6 NTTs + scaling + pointwise
+  const double abc = 4.0 * (double)n + (double)nvars;                        // nnz ~ 3n products + Cz
+  return (ntt + abc) / 0.7;
+}
+
+static int shard_policy() {            // 0 = line, 1 = uniform, 2 = g2own
+  static int v = -1;
+  if (v < 0) {
     const char* e = getenv("G16_SHARD_POLICY");
-    uniform = (e && e[0] == 'u') ? 1 : 0;
+    v = (e && e[0] == 'u') ? 1 : (e && e[0] == 'g') ? 2 : 0;
   }
-  if (G < 4 || uniform) {                      // measured: 13.1 vs 12.9 ms at G = 2, 8.1 vs 8.6 at 4, 5.5 vs 5.9 at 8
-    shard_range(nvars, k, G, out[0], out[1]);
-    shard_range(n, k, G, out[2], out[3]);
-    return;
+  return v;
+}
+
+// ranks [0, G) share the line [H (+ quotient) | arrays...]; out[k] receives the ranges
+static void plan_line(size_t nvars, size_t n, int G, const bool with_b2, std::vector<ShardPlan>& out, int first_rank) {
+  const double cost[4] = {msm_cost(nvars, false), msm_cost(nvars, false), msm_cost(nvars, false),
+                          with_b2 ? msm_cost(nvars, true) : 0.0};
+  const double Wh = msm_cost(n, false), Q = quotient_cost(n, nvars);
+  const double Ww = cost[0] + cost[1] + cost[2] + cost[3];
+  // number of H ranks
+  int best_m = 1;
+  double best = 1e300, bestL = 0.0;
+  for (int m = 1; m <= G; m++) {
+    const double Th = Q + Wh / m;
+    double L = (Ww + m * Th) / G, worst;
+    if (L >= Th) worst = L;
+    else if (m < G) {
+      L = Ww / (G - m);
+      worst = Th > L ? Th : L;
+    } else continue;
+    if (worst < best * 0.995) {          // ties go to fewer redundant quotients
+      best = worst;
+      best_m = m;
+      bestL = L;
+    }
   }
-  const int m = G >= 8 ? G / 4 : 1;
-  const double cw = 13.0, ch = 2.05, cq = 1.4;
-  const double d = (cq + ch / m) / cw;
-  double fh = (1.0 - (G - m) * d) / G;
-  if (fh < 0) fh = 0;
-  const double fo = (1.0 - m * fh) / (G - m);
-  auto bound = [&](int idx) -> size_t {
-    if (idx >= G) return nvars;
-    double f = idx <= m ? idx * fh : m * fh + (idx - m) * fo;
-    size_t b = (size_t)(f * (double)nvars + 0.5);
-    return b > nvars ? nvars : b;
-  };
-  out[0] = bound(k);
-  out[1] = bound(k + 1);
-  if (out[1] < out[0]) out[1] = out[0];
-  if (k < m) shard_range(n, k, m, out[2], out[3]);
-  else out[2] = out[3] = n;
+  const int m = best_m;
+  const double Th = Q + Wh / m;
+  // walk the witness arrays; cut positions are snapped to array boundaries when within 1/8 of one
+  double pos = 0.0;                      // position on the line of witness work, in cost units
+  size_t cur_arr = 0, cur_pt = 0;        // next unassigned point
+  for (int k = 0; k < G; k++) {
+    ShardPlan& p = out[first_rank + k];
+    if (k < m) shard_range(n, k, m, p.h_lo, p.h_hi);
+    double cap = k < m ? (bestL > Th ? bestL - Th : 0.0) : bestL;
+    if (k == G - 1) cap = 1e300;         // the last rank takes the remainder
+    double end = pos + cap;
+    size_t* lo[4] = {&p.a1_lo, &p.b1_lo, &p.c1_lo, &p.b2_lo};
+    size_t* hi[4] = {&p.a1_hi, &p.b1_hi, &p.c1_hi, &p.b2_hi};
+    while (cur_arr < 4 && pos < end) {
+      if (cost[cur_arr] <= 0.0) {
+        cur_arr++;
+        cur_pt = 0;
+        continue;
+      }
+      const double per_pt = cost[cur_arr] / (double)nvars;
+      const double room = end - pos;
+      size_t take = nvars - cur_pt;
+      if ((double)take * per_pt > room) {
+        take = (size_t)(room / per_pt);
+        const size_t snap = nvars / 8;                                        // pieces below a tenth of an array: not worth a sort + reduction
+        if (take <= snap) take = 0;                                          // a sliver: leave it to the next rank
+        else if (nvars - (cur_pt + take) <= snap) take = nvars - cur_pt;     // would leave a sliver behind
+      }
+      if (take == 0) break;
+      *lo[cur_arr] = cur_pt;
+      *hi[cur_arr] = cur_pt + take;
+      pos += (double)take * per_pt;
+      cur_pt += take;
+      if (cur_pt == nvars) {
+        cur_arr++;
+        cur_pt = 0;
+      } else break;                      // this rank is full
+    }
+  }
+}
+
+void shard_plan(size_t nvars, size_t npubs, size_t n, int k, int G, ShardPlan& out) {
+  (void)npubs;
+  std::vector<ShardPlan> all((size_t)G);
+  for (auto& p : all) memset(&p, 0, sizeof(p));
+  const int policy = shard_policy();
+  if (G == 1 || policy == 1) {
+    for (int r = 0; r < G; r++) {
+      ShardPlan& p = all[r];
+      shard_range(nvars, r, G, p.a1_lo, p.a1_hi);
+      p.b1_lo = p.c1_lo = p.b2_lo = p.a1_lo;
+      p.b1_hi = p.c1_hi = p.b2_hi = p.a1_hi;
+      shard_range(n, r, G, p.h_lo, p.h_hi);
+    }
+  } else if (policy == 2) {
+    plan_line(nvars, n, G - 1, false, all, 0);
+    all[G - 1].b2_lo = 0;
+    all[G - 1].b2_hi = nvars;
+  } else {
+    plan_line(nvars, n, G, true, all, 0);
+  }
+  out = all[k];
 }
 
 // raw points of [lo, hi) -> temporary device buffer.  The copy is issued on the consumer's stream: a plain
 // cudaMemcpy from pageable memory returns once the data is staged and is ordered only against the legacy
 // default stream, which non-blocking streams do not wait for.
-static void upload(DevBuf& dst, const void* src, size_t elem, size_t lo, size_t hi, int mem_kind,
-                   cudaStream_t stream) {
+static void upload(void* dst, const void* src, size_t elem, size_t lo, size_t hi, int mem_kind, cudaStream_t stream) {
   size_t bytes = (hi - lo) * elem;
-  dst.ensure(bytes ? bytes : 16);
   if (!bytes) return;
   G16_REQUIRE(src != nullptr, "zkey view: missing point array");
   const char* s = reinterpret_cast<const char*>(src) + lo * elem;
-  G16_CUDA(cudaMemcpyAsync(dst.p, s, bytes,
-                           mem_kind == G16_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+  G16_CUDA(cudaMemcpyAsync(dst, s, bytes, mem_kind == G16_MEM_DEVICE ? cudaMemcpyDefault : cudaMemcpyHostToDevice,
+                           stream));
 }
 
+// Loader validation (groth16/bn128/io.nim:228-236 loadPointG1/G2 -> curves.nim:54-91 mkG1/mkG2): every point of a
+// prover array must satisfy the curve equation (G1: y^2 = x^3 + 3; G2: the twist y^2 = x^3 + 3/(9+u)) or be the
+// point at infinity (0,0).  bad[0] receives the smallest offending index (0xffffffff = none).
 template <class F>
-static void make_table(DevBuf& table, const void* src, size_t lo, size_t hi, size_t pad_front, int c, int mem_kind,
-                       cudaStream_t stream) {
-  size_t n = (hi - lo) + pad_front;
-  table.ensure(n ? (size_t)msm_num_windows(c) * n * sizeof(Affine<F>) : 16);
+struct CurveB;
+template <>
+struct CurveB<Fp> {
+  static __device__ __forceinline__ Fp b() {          // 3 in Montgomery form
+    Fp o = Fp::one();
+    return fadd(fadd(o, o), o);
+  }
+};
+template <>
+struct CurveB<Fp2> {
+  static __device__ __forceinline__ Fp2 b() {         // curves.nim:75-77 twistCoeffB, standard form -> Montgomery
+    Fp b1, bu;
+    const uint32_t w1[8] = {0x24a138e5u, 0x3267e6dcu, 0x59dbefa3u, 0xb5b4c5e5u, 0x1be06ac3u, 0x81be1899u, 0xceb8aaaeu, 0x2b149d40u};
+    const uint32_t wu[8] = {0x85c315d2u, 0xe4a2bd06u, 0xe52d1852u, 0xa74fa084u, 0xeed8fdf4u, 0xcd2cafadu, 0x3af0fed4u, 0x009713b0u};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      b1.v[i] = w1[i];
+      bu.v[i] = wu[i];
+    }
+    Fp2 r;
+    r.c0 = to_mont(b1);
+    r.c1 = to_mont(bu);
+    return r;
+  }
+};
+template <class P>
+static __device__ __forceinline__ bool canonical(const Fe<P>& a) {     // a < modulus
+#pragma unroll
+  for (int k = 7; k >= 0; k--)
+    if (a.v[k] != P::mod(k)) return a.v[k] < P::mod(k);
+  return false;
+}
+static __device__ __forceinline__ bool canonical(const Fp2& a) { return canonical(a.c0) && canonical(a.c1); }
+
+template <class F>
+__global__ void __launch_bounds__(128) k_check_on_curve(const Affine<F>* __restrict__ pts, uint32_t n, uint32_t* bad) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> p = ldv(pts + i);
+  if (aff_is_inf(p)) return;
+  bool ok = canonical(p.x) && canonical(p.y);
+  if (ok) {
+    F lhs = fsqr(p.y);
+    F rhs = fadd(fmul(fsqr(p.x), p.x), CurveB<F>::b());
+    ok = feq(lhs, rhs);
+  }
+  if (!ok) atomicMin(bad, i);
+}
+
+struct TableJob {                       // validation results are read once, after all arrays have been enqueued
+  const char* name;
+  size_t lo;
+  uint32_t* bad_dev;
+};
+
+// one prover array range -> window table (precomp) or padded plain points, validated on the way
+template <class F>
+static void make_table(DevBuf& table, const void* src, size_t lo, size_t hi, size_t pad_front, int c, bool precomp,
+                       bool validate, const char* name, int mem_kind, DevBuf& raw, uint32_t* bad_dev,
+                       std::vector<TableJob>& jobs, cudaStream_t copy_stream, cudaEvent_t copied, cudaStream_t stream) {
+  const size_t n = (hi - lo) + pad_front;
+  const size_t nwin = precomp ? (size_t)msm_num_windows(c) : 1;
+  table.ensure(n ? nwin * n * sizeof(Affine<F>) : 16);
   if (!n) return;
-  DevBuf raw;
-  upload(raw, src, sizeof(Affine<F>), lo, hi, mem_kind, stream);
-  msm_build_table<F>(raw.as<Affine<F>>(), hi - lo, pad_front, c, table.as<Affine<F>>(), stream);
-  G16_CUDA(cudaStreamSynchronize(stream));   // raw is released on return
+  Affine<F>* pts;
+  if (precomp) {
+    raw.ensure((hi - lo) * sizeof(Affine<F>) + 16);
+    pts = raw.as<Affine<F>>();
+  } else {
+    pts = table.as<Affine<F>>() + pad_front;
+    if (pad_front) G16_CUDA(cudaMemsetAsync(table.p, 0, pad_front * sizeof(Affine<F>), stream));
+  }
+  // the copy runs on its own stream: the H2D of this array overlaps with the table kernel of the previous one
+  upload(pts, src, sizeof(Affine<F>), lo, hi, mem_kind, copy_stream);
+  G16_CUDA(cudaEventRecord(copied, copy_stream));
+  G16_CUDA(cudaStreamWaitEvent(stream, copied, 0));
+  if (validate && hi > lo) {
+    G16_CUDA(cudaMemsetAsync(bad_dev, 0xff, 4, stream));
+    k_check_on_curve<F><<<div_up(hi - lo, 128), 128, 0, stream>>>(pts, (uint32_t)(hi - lo), bad_dev);
+    G16_LAUNCH_CHECK();
+    jobs.push_back(TableJob{name, lo, bad_dev});
+  }
+  if (precomp) msm_build_table<F>(pts, hi - lo, pad_front, c, table.as<Affine<F>>(), stream);
 }
 
 Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_in)
@@ -383,45 +567,107 @@ Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_
   log_n = zk.log_domain;
   flavour = zk.flavour;
   n = (size_t)1 << log_n;
-  cudaStream_t main_ = nullptr;
+  precomp = !(zk.flags & G16_ZKEY_ONE_SHOT);
+  if (const char* e = getenv("G16_LAYOUT")) precomp = e[0] != 'p';     // "plain" / "table": A/B runs
+  const bool validate = !(zk.flags & G16_ZKEY_TRUSTED);
+  cudaStream_t main_ = nullptr, copy_ = nullptr;
   G16_CUDA(cudaStreamCreateWithFlags(&main_, cudaStreamNonBlocking));
-  // this context's contiguous ranges (msm.nim:107-111): witness-indexed arrays and the H array
-  {
-    size_t rg[4];
-    shard_ranges(nvars, n, shard_index, shard_count, rg);
-    v_lo = rg[0];
-    v_hi = rg[1];
-    h_lo = rg[2];
-    h_hi = rg[3];
-  }
-  const size_t nv = v_hi - v_lo, nh = h_hi - h_lo;
-  if (nv) gw = msm_geometry(nv, msm_pick_window(nv, true), true);
-  if (nh) gh = msm_geometry(nh, msm_pick_window(nh, true), true);
-  make_table<Fp>(tabA1, zk.points_a1, v_lo, v_hi, 0, gw.c ? gw.c : 4, zk.mem_kind, main_);
-  make_table<Fp>(tabB1, zk.points_b1, v_lo, v_hi, 0, gw.c ? gw.c : 4, zk.mem_kind, main_);
-  make_table<Fp2>(tabB2, zk.points_b2, v_lo, v_hi, 0, gw.c ? gw.c : 4, zk.mem_kind, main_);
-  {
-    // C1[j - npubs - 1] multiplies witness[j] (prover.nim:262-264): pad so that table index == witness index
-    size_t first = (size_t)npubs + 1;
-    size_t from = v_lo > first ? v_lo : first;            // first witness index of this shard with a C point
-    size_t pad = v_hi > from ? from - v_lo : nv;
-    size_t c_lo = from - first, c_hi = v_hi > from ? v_hi - first : c_lo;
-    make_table<Fp>(tabC1, zk.points_c1, c_lo, c_hi, pad, gw.c ? gw.c : 4, zk.mem_kind, main_);
-  }
-  make_table<Fp>(tabH1, zk.points_h1, h_lo, h_hi, 0, gh.c ? gh.c : 4, zk.mem_kind, main_);
+  G16_CUDA(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking));
+  cudaEvent_t copied[6];
+  for (auto& e : copied) G16_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  int ncopied = 0;
+  shard_plan(nvars, npubs, n, shard_index, shard_count, plan);
 
-  // coefficient list -> CSR rows (once per zkey)
-  {
+  // witness-indexed pieces grouped by range (same range -> one sorter run, fused G1 launches)
+  struct Piece { int which; size_t lo, hi; };
+  const Piece pieces[4] = {{0, plan.a1_lo, plan.a1_hi}, {1, plan.b1_lo, plan.b1_hi}, {2, plan.c1_lo, plan.c1_hi},
+                           {3, plan.b2_lo, plan.b2_hi}};
+  for (const Piece& pc : pieces) {
+    if (pc.hi <= pc.lo) continue;
+    G16_REQUIRE(pc.hi <= nvars, "shard plan out of range");
+    WitnessGroup* g = nullptr;
+    for (auto& q : groups)
+      if (q->lo == pc.lo && q->hi == pc.hi) g = q.get();
+    if (!g) {
+      groups.emplace_back(new WitnessGroup());
+      g = groups.back().get();
+      g->lo = pc.lo;
+      g->hi = pc.hi;
+      g->geom = msm_geometry(pc.hi - pc.lo, msm_pick_window(pc.hi - pc.lo, precomp), precomp);
+    }
+    if (pc.which == 3) g->has_b2 = true;
+    else g->which1[g->nsets1++] = pc.which;
+    if (pc.which < 2) owns_ab = true;
+  }
+  // the group with the G2 MSM (the longest kernel) is sorted and launched first
+  for (size_t i = 1; i < groups.size(); i++)
+    if (groups[i]->has_b2) std::swap(groups[0], groups[i]);
+  const size_t nh = plan.h_hi - plan.h_lo;
+  if (nh) gh = msm_geometry(nh, msm_pick_window(nh, precomp), precomp);
+
+  // uploads, validation and table building; one raw staging buffer per array so that the copies of the next array
+  // overlap with the table kernel of the previous one (the copies are ordered on the same stream, the buffers
+  // are released at the end)
+  std::vector<TableJob> jobs;
+  DevBuf bad;
+  bad.ensure(8 * 4);
+  std::vector<std::unique_ptr<DevBuf>> raws;
+  int nbad = 0;
+  auto raw = [&]() -> DevBuf& {
+    raws.emplace_back(new DevBuf());
+    return *raws.back();
+  };
+  static const char* names[5] = {"pointsA1", "pointsB1", "pointsC1", "pointsB2", "pointsH1"};
+  for (auto& gp : groups) {
+    WitnessGroup& g = *gp;
+    for (int s = 0; s < g.nsets1; s++) {
+      const int which = g.which1[s];
+      if (which < 2) {
+        make_table<Fp>(g.tab1[s], which == 0 ? zk.points_a1 : zk.points_b1, g.lo, g.hi, 0, g.geom.c, precomp, validate,
+                       names[which], zk.mem_kind, raw(), bad.as<uint32_t>() + nbad++, jobs, copy_, copied[ncopied++], main_);
+      } else {
+        // C1[j - npubs - 1] multiplies witness[j] (prover.nim:262-264): pad so that table index == witness index
+        const size_t first = (size_t)npubs + 1;
+        const size_t from = g.lo > first ? g.lo : first;            // first witness index of this piece with a C point
+        const size_t pad = g.hi > from ? from - g.lo : g.hi - g.lo;
+        const size_t c_lo = from - first, c_hi = g.hi > from ? g.hi - first : c_lo;
+        make_table<Fp>(g.tab1[s], zk.points_c1, c_lo, c_hi, pad, g.geom.c, precomp, validate, names[2], zk.mem_kind,
+                       raw(), bad.as<uint32_t>() + nbad++, jobs, copy_, copied[ncopied++], main_);
+      }
+    }
+    if (g.has_b2)
+      make_table<Fp2>(g.tabB2, zk.points_b2, g.lo, g.hi, 0, g.geom.c, precomp, validate, names[3], zk.mem_kind, raw(),
+                      bad.as<uint32_t>() + nbad++, jobs, copy_, copied[ncopied++], main_);
+  }
+  make_table<Fp>(tabH1, zk.points_h1, plan.h_lo, plan.h_hi, 0, gh.c ? gh.c : 4, precomp, validate, names[4], zk.mem_kind,
+                 raw(), bad.as<uint32_t>() + nbad++, jobs, copy_, copied[ncopied++], main_);
+
+  // witness intervals this shard reads: everything when it runs buildABC, else the union of its groups
+  if (nh) witness_needs.emplace_back((size_t)0, (size_t)nvars);
+  else {
+    std::vector<std::pair<size_t, size_t>> iv;
+    for (auto& gp : groups) iv.emplace_back(gp->lo, gp->hi);
+    std::sort(iv.begin(), iv.end());
+    for (auto& x : iv) {
+      if (!witness_needs.empty() && x.first <= witness_needs.back().second) {
+        if (x.second > witness_needs.back().second) witness_needs.back().second = x.second;
+      } else witness_needs.push_back(x);
+    }
+  }
+
+  // coefficient list -> CSR rows (once per zkey; only ranks that own H points run buildABC)
+  if (nh) {
     size_t rec = zk.coeff_format == G16_COEFF_PACKED44_R2 ? 44 : 48;
-    DevBuf raw;
-    raw.ensure(zk.ncoeffs * rec + 16);
+    DevBuf& rawc = raw();
+    rawc.ensure(zk.ncoeffs * rec + 16);
     if (zk.ncoeffs) {
       G16_REQUIRE(zk.coeffs != nullptr, "zkey view: missing coefficient list");
-      G16_CUDA(cudaMemcpyAsync(raw.p, zk.coeffs, zk.ncoeffs * rec,
-                               zk.mem_kind == G16_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                               main_));
+      G16_CUDA(cudaMemcpyAsync(rawc.p, zk.coeffs, zk.ncoeffs * rec,
+                               zk.mem_kind == G16_MEM_DEVICE ? cudaMemcpyDefault : cudaMemcpyHostToDevice, copy_));
+      G16_CUDA(cudaEventRecord(copied[ncopied], copy_));
+      G16_CUDA(cudaStreamWaitEvent(main_, copied[ncopied], 0));
     }
-    coeffs_to_csr(csr, raw.p, zk.ncoeffs, (int)zk.coeff_format, (int)log_n, nvars, main_);
+    coeffs_to_csr(csr, rawc.p, zk.ncoeffs, (int)zk.coeff_format, (int)log_n, nvars, main_);
   }
 
   SpecPointsDev sp;
@@ -441,17 +687,30 @@ Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_
   k_delta_tables<<<1, 128, 0, main_>>>(spec.as<SpecPointsDev>(), dtab1.as<G1XYZZ>(), dtab2.as<G2XYZZ>(),
                                        atab1.as<G1XYZZ>(), btab1.as<G1XYZZ>());
   G16_LAUNCH_CHECK();
-  G16_CUDA(cudaStreamSynchronize(main_));
-
-  ntt_prepare((int)log_n, main_);
+  if (nh) ntt_prepare((int)log_n, main_);
+  // validation verdicts (one small copy), then the staging buffers go away
+  uint32_t bad_host[8];
+  G16_CUDA(cudaMemcpyAsync(bad_host, bad.p, sizeof(bad_host), cudaMemcpyDeviceToHost, main_));
   G16_CUDA(cudaStreamSynchronize(main_));
   cudaStreamDestroy(main_);
+  cudaStreamDestroy(copy_);
+  for (auto& e : copied) cudaEventDestroy(e);
+  for (const TableJob& j : jobs) {
+    const uint32_t idx = bad_host[j.bad_dev - bad.as<uint32_t>()];
+    // curves.nim:95-107 mkG1 / mkG2 assert texts
+    if (idx != 0xffffffffu)
+      throw Error(G16_ERR_ARG, std::string(j.name) + "[" + std::to_string(j.lo + idx) + "]: " +
+                                   (strcmp(j.name, "pointsB2") == 0 ? "mkG2: not a G2 curve point"
+                                                                     : "mkG1: not a G1 curve point"));
+  }
 }
 
 
 size_t Resident::bytes() const {
-  return tabA1.bytes + tabB1.bytes + tabC1.bytes + tabH1.bytes + tabB2.bytes + csr.ptr.bytes + csr.other.bytes +
-         csr.vals.bytes + dtab1.bytes + dtab2.bytes + atab1.bytes + btab1.bytes;
+  size_t t = tabH1.bytes + csr.ptr.bytes + csr.other.bytes + csr.vals.bytes + dtab1.bytes + dtab2.bytes + atab1.bytes +
+             btab1.bytes;
+  for (auto& g : groups) t += g->tab1[0].bytes + g->tab1[1].bytes + g->tab1[2].bytes + g->tabB2.bytes;
+  return t;
 }
 
 void Prover::init_slot() {
@@ -471,16 +730,24 @@ void Prover::init_slot() {
   G16_CUDA(cudaStreamCreateWithPriority(&st_[2], cudaStreamNonBlocking, pr[2]));
   G16_CUDA(cudaStreamCreateWithPriority(&st_mask_, cudaStreamNonBlocking, prio_hi));
   for (int i = 0; i < 24; i++) G16_CUDA(cudaEventCreate(&ev_[i]));
+  for (auto& g : R->groups) {
+    (void)g;
+    gw_.emplace_back(new GroupWork());
+  }
+  for (int i = 0; i < 4; i++) G16_CUDA(cudaEventCreateWithFlags(&gev_[i], cudaEventDisableTiming));
 
   witness_.ensure((size_t)R->nvars * sizeof(Fr));
-  abc_.ensure(3 * R->n * sizeof(Fr));
-  qs_.ensure(R->n * sizeof(Fr));
+  if (R->plan.h_hi > R->plan.h_lo) {                 // only ranks that own H points run buildABC and the quotient
+    abc_.ensure(3 * R->n * sizeof(Fr));
+    qs_.ensure(R->n * sizeof(Fr));
+  }
   results_.ensure(sizeof(MsmResults));
   G16_CUDA(cudaMemset(results_.p, 0, sizeof(MsmResults)));   // all-zero XYZZ == infinity (empty shards)
   mask_.ensure(sizeof(MaskTerms));
-  proof_.ensure(sizeof(g16_proof));
+  proof_.ensure(sizeof(ProofOut));
+  G16_CUDA(cudaMemset(proof_.p, 0, sizeof(ProofOut)));
   early_.ensure(sizeof(G1XYZZ) * (1 + 512));      // partial pi_c + the two doubling tables of k_assemble_early
-  G16_CUDA(cudaMallocHost(reinterpret_cast<void**>(&proof_pinned_), sizeof(g16_proof)));
+  G16_CUDA(cudaMallocHost(reinterpret_cast<void**>(&proof_pinned_), sizeof(ProofOut)));
 }
 
 Prover::Prover(const g16_zkey_view& zk, int shard_index, int shard_count)
@@ -491,14 +758,17 @@ Prover::Prover(const g16_zkey_view& zk, int shard_index, int shard_count)
 Prover::Prover(std::shared_ptr<Resident> resident) : R(std::move(resident)) { init_slot(); }
 
 size_t Prover::resident_bytes() const {
-  return R->bytes() + witness_.bytes + abc_.bytes + qs_.bytes + sortW_.workspace_bytes() +
-         sortH_.workspace_bytes() + accW_.workspace_bytes() + accH_.workspace_bytes() + accB2_.workspace_bytes();
+  size_t t = R->bytes() + witness_.bytes + abc_.bytes + qs_.bytes + sortH_.workspace_bytes() + accH_.workspace_bytes();
+  for (auto& g : gw_) t += g->sort.workspace_bytes() + g->acc1.workspace_bytes() + g->acc2.workspace_bytes();
+  return t;
 }
 
 Prover::~Prover() {
   cudaDeviceSynchronize();
   for (int i = 0; i < 24; i++)
     if (ev_[i]) cudaEventDestroy(ev_[i]);
+  for (int i = 0; i < 4; i++)
+    if (gev_[i]) cudaEventDestroy(gev_[i]);
   for (int i = 0; i < 3; i++)
     if (st_[i]) cudaStreamDestroy(st_[i]);
   if (st_mask_) cudaStreamDestroy(st_mask_);
@@ -524,23 +794,40 @@ float Prover::timer_stop() {
   return ms;
 }
 
+// Only the witness intervals this shard reads travel (Resident::witness_needs): everything on a rank that runs
+// buildABC, else the ranges of its MSM pieces -- on 8 GPUs most ranks read an eighth to a third of the witness.
 void Prover::load_witness(const void* w, int form, int mem_kind) {
   G16_REQUIRE(w != nullptr, "witness is null");
   G16_REQUIRE(form == G16_FORM_MONT || form == G16_FORM_STD, "unknown witness form");
-  size_t bytes = (size_t)R->nvars * sizeof(Fr);
-  cudaMemcpyKind kind = mem_kind == G16_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  cudaMemcpyKind kind = mem_kind == G16_MEM_DEVICE ? cudaMemcpyDefault : cudaMemcpyHostToDevice;
   G16_CUDA(cudaEventRecord(ev_[20], main_));
-  if (form == G16_FORM_STD) {
-    G16_CUDA(cudaMemcpyAsync(witness_.p, w, bytes, kind, main_));
-  } else {
-    staging_.ensure(bytes);
-    G16_CUDA(cudaMemcpyAsync(staging_.p, w, bytes, kind, main_));
-    fr_from_mont(staging_.as<Fr>(), witness_.as<Fr>(), R->nvars, main_);
+  if (form == G16_FORM_MONT) staging_.ensure((size_t)R->nvars * sizeof(Fr));
+  h2d_bytes_ = 0;
+  for (const auto& iv : R->witness_needs) {
+    const size_t cnt = iv.second - iv.first, bytes = cnt * sizeof(Fr);
+    if (!cnt) continue;
+    const Fr* src = reinterpret_cast<const Fr*>(w) + iv.first;
+    Fr* dst = witness_.as<Fr>() + iv.first;
+    if (form == G16_FORM_STD) {
+      if (src != dst) G16_CUDA(cudaMemcpyAsync(dst, src, bytes, kind, main_));
+      fr_reduce_std(dst, cnt, main_);                // values >= r (malformed .wtns) are reduced like io.nim:141-145
+    } else {
+      Fr* stg = staging_.as<Fr>() + iv.first;
+      G16_CUDA(cudaMemcpyAsync(stg, src, bytes, kind, main_));
+      fr_from_mont(stg, dst, cnt, main_);
+    }
+    h2d_bytes_ += bytes;
   }
   G16_CUDA(cudaEventRecord(ev_[21], main_));
 }
 
 void Prover::run_msms(g16_stats* stats) {
+  // an announced mask serves ONE set of partial sums: without a new g16_ctx_set_mask the records are plain again
+  if (masked_partials_ && mask_used_) {
+    masked_partials_ = false;
+    mask_started_ = false;
+  }
+  mask_used_ = true;
   // empty shards write nothing: start every proof from infinity (all-zero XYZZ)
   G16_CUDA(cudaMemsetAsync(results_.p, 0, sizeof(MsmResults), main_));
   // ev_[0]: witness ready on main_; every worker stream waits for it
@@ -548,16 +835,16 @@ void Prover::run_msms(g16_stats* stats) {
   for (int i = 0; i < 3; i++) G16_CUDA(cudaStreamWaitEvent(st_[i], ev_[0], 0));
   MsmResults* res = results_.as<MsmResults>();
   const Fr* w = witness_.as<Fr>();
-  const size_t nv = R->v_hi - R->v_lo, nh = R->h_hi - R->h_lo;
+  const size_t nh = R->plan.h_hi - R->plan.h_lo;
 
-  // stream 0: ABC -> quotient -> sort of qs -> MSM over the H table   (prover.nim:245-260, 301)
+  // stream 0: ABC -> quotient -> sort of qs -> MSM over the H points   (prover.nim:245-260, 301)
   G16_CUDA(cudaEventRecord(ev_[1], st_[0]));
   if (nh) build_abc(R->csr, w, abc_.as<Fr>(), (int)R->log_n, st_[0]);      // ranks without H points skip the chain
   G16_CUDA(cudaEventRecord(ev_[2], st_[0]));
   if (nh) quotient(abc_.as<Fr>(), qs_.as<Fr>(), (int)R->log_n, (int)R->flavour, st_[0]);
   G16_CUDA(cudaEventRecord(ev_[3], st_[0]));
   if (nh) {
-    sortH_.run(qs_.as<Fr>() + R->h_lo, true, R->gh, st_[0]);
+    sortH_.run(qs_.as<Fr>() + R->plan.h_lo, true, R->gh, st_[0]);
     MsmPointSet<Fp> hs;
     hs.points = R->tabH1.as<G1Affine>();
     hs.result = &res->h1;
@@ -565,28 +852,49 @@ void Prover::run_msms(g16_stats* stats) {
   }
   G16_CUDA(cudaEventRecord(ev_[4], st_[0]));
 
-  // stream 1: one digit/sort pass over the witness, then A1, B1, C1 in the same launches
-  // (prover.nim:282, 288, 302; zs = witness[npubs+1 ..] through the padded C1 table)
+  // stream 1: per group one digit/sort pass over its witness range, then its G1 sets in the same launches
+  // (prover.nim:282, 288, 302; zs = witness[npubs+1 ..] through the padded C1 table); stream 2: the G2 set
+  // (prover.nim:294) over the same sorted pairs.  Every group writes distinct result fields.
   G16_CUDA(cudaEventRecord(ev_[5], st_[1]));
-  if (nv) sortW_.run(w + R->v_lo, false, R->gw, st_[1]);
-  G16_CUDA(cudaEventRecord(ev_[6], st_[1]));
-  G16_CUDA(cudaStreamWaitEvent(st_[2], ev_[6], 0));
-  if (nv) {
-    MsmPointSet<Fp> ws[3];
-    ws[0].points = R->tabA1.as<G1Affine>();
-    ws[0].result = &res->a1;
-    ws[1].points = R->tabB1.as<G1Affine>();
-    ws[1].result = &res->b1;
-    ws[2].points = R->tabC1.as<G1Affine>();
-    ws[2].result = &res->c1;
-    accW_.run(sortW_, ws, 3, st_[1]);
+  for (size_t gi = 0; gi < R->groups.size(); gi++) {
+    const WitnessGroup& g = *R->groups[gi];
+    GroupWork& gw = *gw_[gi];
+    gw.sort.run(w + g.lo, false, g.geom, st_[1]);
+    if (gi == 0) G16_CUDA(cudaEventRecord(ev_[6], st_[1]));
+    if (g.has_b2) {
+      G16_CUDA(cudaEventRecord(gev_[gi], st_[1]));
+      G16_CUDA(cudaStreamWaitEvent(st_[2], gev_[gi], 0));
+      G16_CUDA(cudaEventRecord(ev_[8], st_[2]));
+      MsmPointSet<Fp2> bs;
+      bs.points = g.tabB2.as<G2Affine>();
+      bs.result = &res->b2;
+      gw.acc2.run(gw.sort, &bs, 1, st_[2]);
+      G16_CUDA(cudaEventRecord(ev_[9], st_[2]));
+    }
+    if (g.nsets1) {
+      MsmPointSet<Fp> ws[3];
+      for (int k = 0; k < g.nsets1; k++) {
+        ws[k].points = g.tab1[k].as<G1Affine>();
+        ws[k].result = g.which1[k] == 0 ? &res->a1 : g.which1[k] == 1 ? &res->b1 : &res->c1;
+      }
+      gw.acc1.run(gw.sort, ws, g.nsets1, st_[1]);
+    }
+  }
+  if (R->groups.empty()) G16_CUDA(cudaEventRecord(ev_[6], st_[1]));
+  bool any_b2 = false;
+  for (auto& g : R->groups) any_b2 = any_b2 || g->has_b2;
+  if (!any_b2) {
+    G16_CUDA(cudaEventRecord(ev_[8], st_[2]));
+    G16_CUDA(cudaEventRecord(ev_[9], st_[2]));
   }
   G16_CUDA(cudaEventRecord(ev_[7], st_[1]));
   if (masked_partials_) {
     // this shard's share of s ** pi_a + r ** rho, folded into its c1 partial while B2 / H are still in flight
-    G16_CUDA(cudaStreamWaitEvent(st_[1], ev_[23], 0));
-    k_shard_early<<<1, 256, 0, st_[1]>>>(results_.as<MsmResults>(), mask_.as<MaskTerms>(), early_.as<G1XYZZ>() + 1);
-    G16_LAUNCH_CHECK();
+    if (R->owns_ab) {
+      G16_CUDA(cudaStreamWaitEvent(st_[1], ev_[23], 0));
+      k_shard_early<<<1, 256, 0, st_[1]>>>(results_.as<MsmResults>(), mask_.as<MaskTerms>(), early_.as<G1XYZZ>() + 1);
+      G16_LAUNCH_CHECK();
+    }
   } else if (mask_started_ && R->shard_count == 1) {
     // the MSM-dependent scalar multiplications start now and overlap with the B2 / H work still in flight
     G16_CUDA(cudaStreamWaitEvent(st_[1], ev_[23], 0));
@@ -595,16 +903,6 @@ void Prover::run_msms(g16_stats* stats) {
     G16_LAUNCH_CHECK();
     early_done_ = true;
   }
-
-  // stream 2: pi_B MSM in G2 over the same sorted pairs (prover.nim:294)
-  G16_CUDA(cudaEventRecord(ev_[8], st_[2]));
-  if (nv) {
-    MsmPointSet<Fp2> bs;
-    bs.points = R->tabB2.as<G2Affine>();
-    bs.result = &res->b2;
-    accB2_.run(sortW_, &bs, 1, st_[2]);
-  }
-  G16_CUDA(cudaEventRecord(ev_[9], st_[2]));
 
   for (int i = 0; i < 3; i++) {
     G16_CUDA(cudaEventRecord(ev_[13 + i], st_[i]));
@@ -627,9 +925,17 @@ void Prover::collect_stats(g16_stats* stats) {
 }
 
 void Prover::partials_to_affine_async(void* partials_dev) {
-  k_partials_to_affine<<<1, 160, 0, main_>>>(results_.as<MsmResults>(), reinterpret_cast<PartialsAffine*>(partials_dev));
+  k_partials_to_affine<<<1, 160, 0, main_>>>(results_.as<MsmResults>(), reinterpret_cast<PartialsAffine*>(partials_dev),
+                                             masked_partials_ ? 1ull : 0ull, masked_partials_ ? mask_hash_ : 0ull);
   G16_LAUNCH_CHECK();
   G16_CUDA(cudaEventRecord(ev_[10], main_));
+}
+void Prover::order_stream(cudaStream_t ext, int direction) {
+  if (direction == 0) G16_CUDA(cudaStreamWaitEvent(ext, ev_[10], 0));
+  else {
+    G16_CUDA(cudaEventRecord(ev_[11], ext));
+    G16_CUDA(cudaStreamWaitEvent(main_, ev_[11], 0));
+  }
 }
 void Prover::partials_wait(g16_stats* stats) {
   G16_CUDA(cudaEventSynchronize(ev_[10]));
@@ -643,7 +949,8 @@ void Prover::partials_to_affine(void* partials_dev) {
 void Prover::sum_partials(const void* gathered_dev, int count) {
   G16_REQUIRE(count >= 1, "need at least one partial record");
   k_sum_partials<<<1, 160, 0, main_>>>(reinterpret_cast<const PartialsAffine*>(gathered_dev), count,
-                                       results_.as<MsmResults>());
+                                       results_.as<MsmResults>(), masked_partials_ ? 1ull : 0ull,
+                                       masked_partials_ ? mask_hash_ : 0ull, &proof_.as<ProofOut>()->status);
   G16_LAUNCH_CHECK();
 }
 
@@ -670,7 +977,12 @@ void Prover::set_mask(const uint64_t r[4], const uint64_t s[4]) {
   start_mask(r, s);
   memcpy(mask_host_, r, 32);
   memcpy(mask_host_ + 4, s, 32);
+  uint64_t h = 1469598103934665603ull;               // FNV-1a over the 64 mask bytes: the tag of masked records
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(mask_host_);
+  for (int i = 0; i < 64; i++) h = (h ^ b[i]) * 1099511628211ull;
+  mask_hash_ = h;
   masked_partials_ = true;
+  mask_used_ = false;
 }
 bool Prover::same_mask(const uint64_t r[4], const uint64_t s[4]) const {
   return r && s && memcmp(mask_host_, r, 32) == 0 && memcmp(mask_host_ + 4, s, 32) == 0;
@@ -697,7 +1009,7 @@ void Prover::finish_async() {
   mask_started_ = false;
   early_done_ = false;
   masked_partials_ = false;
-  G16_CUDA(cudaMemcpyAsync(proof_pinned_, proof_.p, sizeof(g16_proof), cudaMemcpyDeviceToHost, main_));
+  G16_CUDA(cudaMemcpyAsync(proof_pinned_, proof_.p, sizeof(ProofOut), cudaMemcpyDeviceToHost, main_));
   G16_CUDA(cudaEventRecord(ev_[22], main_));
   in_flight_ = true;
 }
@@ -708,7 +1020,10 @@ void Prover::wait(g16_proof* proof, g16_stats* stats) {
   G16_REQUIRE(in_flight_, "no proof in flight on this context");
   G16_CUDA(cudaEventSynchronize(ev_[22]));
   in_flight_ = false;
-  memcpy(proof, proof_pinned_, sizeof(g16_proof));
+  G16_REQUIRE(proof_pinned_->status == 0,
+              "partial records disagree on the mask: g16_ctx_set_mask must be called by every rank of a proof with "
+              "the same r, s, or by none");
+  memcpy(proof, &proof_pinned_->proof, sizeof(g16_proof));
   if (stats) {
     collect_stats(stats);
     cudaEventElapsedTime(&stats->ms_assemble, ev_[19], ev_[22]);

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <memory>
+#include <utility>
+#include <vector>
 #include "../../include/g16b200.h"
 #include "abc.cuh"
 #include "common.cuh"
@@ -13,6 +15,12 @@ namespace g16 {
 struct alignas(16) PartialsAffine {   // == g16_partials
   G1Affine a1, b1, h1, c1;
   G2Affine b2;
+  uint64_t tag[2];                    // [0]: 1 = masked record (c1 = C_k + s A_k + r B1_k); [1]: hash of (r, s) if masked
+};
+struct alignas(16) ProofOut {         // what travels back to the host: the proof and a status word
+  g16_proof proof;
+  uint32_t status;                    // 0 = ok; 1 = the gathered partial records disagree on the mask
+  uint32_t pad[3];
 };
 static_assert(sizeof(PartialsAffine) == sizeof(g16_partials), "g16_partials layout");
 
@@ -36,8 +44,25 @@ struct alignas(16) SpecPointsDev {    // SpecPoints (zkey_types.nim:24-31) neede
   G2Affine beta2, delta2;
 };
 
-// {v_lo, v_hi, h_lo, h_hi} of rank k of G (policy: see prover.cu)
-void shard_ranges(size_t nvars, size_t n, int k, int G, size_t out[4]);
+// What rank k of G owns: a contiguous point range of each of the five MSMs (msm.nim:107-111 chunking, applied per
+// MSM instead of to all of them alike).  A1 / B1 / B2 / C1 ranges are witness indices (C1[j - npubs - 1]
+// multiplies witness[j], prover.nim:262-264); the H range indexes the domain.  Policy and cost model: prover.cu.
+struct ShardPlan {
+  size_t a1_lo, a1_hi, b1_lo, b1_hi, c1_lo, c1_hi, b2_lo, b2_hi, h_lo, h_hi;
+};
+void shard_plan(size_t nvars, size_t npubs, size_t n, int k, int G, ShardPlan& out);
+
+// The witness-indexed pieces of a shard grouped by range: pieces with the same [lo, hi) share one digit/sort pass
+// and (in G1) the accumulate and reduce launches.
+struct WitnessGroup {
+  size_t lo = 0, hi = 0;
+  MsmGeometry geom;
+  int nsets1 = 0;                      // G1 point sets of this group (A1, B1, C1 in that order when present)
+  int which1[3] = {0, 0, 0};           // 0 = A1, 1 = B1, 2 = C1
+  DevBuf tab1[3];
+  bool has_b2 = false;
+  DevBuf tabB2;
+};
 
 // Everything that depends only on the zkey: built once, read-only afterwards, shared by all proofs in flight.
 struct Resident {
@@ -45,10 +70,14 @@ struct Resident {
   int shard_index, shard_count;
   uint32_t nvars, npubs, log_n, flavour;
   size_t n;
-  size_t v_lo, v_hi, h_lo, h_hi;       // this shard's ranges of the witness-indexed arrays and of H1 (msm.nim:107-111)
-  // window tables 2^(c w) P_i: A1, B1, C1 (padded to witness indices), H1 in G1; B2 in G2
-  DevBuf tabA1, tabB1, tabC1, tabH1, tabB2;
-  MsmGeometry gw, gh;
+  ShardPlan plan;                      // this shard's ranges
+  bool precomp = true;                 // window tables (resident key) or plain points (one-shot context)
+  bool owns_ab = false;                // has A1 or B1 points (its masked partials need k_shard_early)
+  // per group: window tables 2^(c w) P_i (or the plain points) of A1, B1, C1 (padded to witness indices) and B2
+  std::vector<std::unique_ptr<WitnessGroup>> groups;
+  DevBuf tabH1;
+  MsmGeometry gh;
+  std::vector<std::pair<size_t, size_t>> witness_needs;   // merged witness index intervals this shard reads
   SparseCsr csr;
   DevBuf spec;                         // SpecPointsDev
   DevBuf dtab1, dtab2;                 // 2^j * delta1 / delta2
@@ -68,6 +97,11 @@ class Prover {
   void run_msms(g16_stats* stats);                     // ABC, quotient, five MSMs -> results_ (asynchronous)
   void collect_stats(g16_stats* stats);                // phase times of the last run (after completion)
   void partials_to_affine(void* partials_dev);         // results_ -> g16_partials (device), synchronous
+  // ordering against a caller-owned stream (the collective between partials and finish): direction 0 makes
+  // `ext` wait for this context's partial record, 1 makes this context wait for what is enqueued on `ext`
+  void order_stream(cudaStream_t ext, int direction);
+  cudaStream_t main_stream() const { return main_; }
+  cudaEvent_t partials_event() const { return ev_[10]; }
   void partials_to_affine_async(void* partials_dev);
   void partials_wait(g16_stats* stats);
   void finish_async();                                 // enqueue assembly + copy-out
@@ -88,20 +122,30 @@ class Prover {
   void timer_start();                 // CUDA event on the context's main stream
   float timer_stop();                 // records, synchronises, returns elapsed ms since timer_start()
   size_t resident_bytes() const;
+  size_t last_witness_bytes() const { return h2d_bytes_; }
+  const ShardPlan& plan() const { return R->plan; }
 
  private:
   void init_slot();
   std::shared_ptr<Resident> R;
-  MsmSorter sortW_, sortH_;
-  MsmAccumulator<Fp> accW_, accH_;
-  MsmAccumulator<Fp2> accB2_;
+  struct GroupWork {                   // per-proof workspaces of one WitnessGroup
+    MsmSorter sort;
+    MsmAccumulator<Fp> acc1;
+    MsmAccumulator<Fp2> acc2;
+  };
+  std::vector<std::unique_ptr<GroupWork>> gw_;
+  MsmSorter sortH_;
+  MsmAccumulator<Fp> accH_;
   DevBuf witness_, staging_, abc_, qs_, results_, mask_, proof_, early_;
-  bool mask_started_ = false, early_done_ = false, in_flight_ = false, masked_partials_ = false;
+  bool mask_started_ = false, early_done_ = false, in_flight_ = false, masked_partials_ = false, mask_used_ = false;
+  uint64_t mask_hash_ = 0;
   uint64_t mask_host_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaStream_t main_ = nullptr, st_mask_ = nullptr, st_[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_[24];
+  cudaEvent_t gev_[4] = {nullptr, nullptr, nullptr, nullptr};   // sort of group i done (the G2 stream waits on it)
+  size_t h2d_bytes_ = 0;                // witness bytes copied by the last load_witness()
   cudaEvent_t tev_[2] = {nullptr, nullptr};
-  g16_proof* proof_pinned_ = nullptr;
+  ProofOut* proof_pinned_ = nullptr;
 };
 
 }  // namespace g16

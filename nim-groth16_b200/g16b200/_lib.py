@@ -18,7 +18,8 @@ class G16Error(AssertionError):
 
 class ZkeyView(C.Structure):
     _fields_ = [("nvars", C.c_uint32), ("npubs", C.c_uint32), ("log_domain", C.c_uint32), ("flavour", C.c_uint32),
-                ("coeff_format", C.c_uint32), ("mem_kind", C.c_uint32), ("ncoeffs", C.c_uint64),
+                ("coeff_format", C.c_uint32), ("mem_kind", C.c_uint32), ("flags", C.c_uint32),
+                ("reserved0", C.c_uint32), ("ncoeffs", C.c_uint64),
                 ("coeffs", C.c_void_p), ("points_a1", C.c_void_p), ("points_b1", C.c_void_p),
                 ("points_b2", C.c_void_p), ("points_c1", C.c_void_p), ("points_h1", C.c_void_p),
                 ("alpha1", C.c_uint64 * 8), ("beta1", C.c_uint64 * 8), ("beta2", C.c_uint64 * 16),
@@ -55,7 +56,8 @@ class SetupOut(C.Structure):
                                           "points_ic", "spec", "dlog_a", "dlog_b", "dlog_k", "dlog_h", "dlog_ic")]
 
 
-PARTIALS_BYTES = 4 * 64 + 128
+PARTIALS_BYTES = 4 * 64 + 128 + 16      # sizeof(g16_partials): five affine sums and the mask tag
+ZKEY_TRUSTED, ZKEY_ONE_SHOT = 1, 2       # g16_zkey_view.flags
 
 # every symbol include/g16b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -63,6 +65,8 @@ SIGNATURES = {
     "g16_version": (C.c_int, []),
     "g16_set_device": (C.c_int, [C.c_int]),
     "g16_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "g16_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "g16_host_unregister": (C.c_int, [C.c_void_p]),
     "g16_msm_g1": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "g16_msm_g2": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "g16_ntt_fr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
@@ -81,7 +85,9 @@ SIGNATURES = {
     "g16_prove_partials_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "g16_prove_partials_wait": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "g16_prove_finish_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
-    "g16_shard_ranges": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
+    "g16_shard_plan": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
+    "g16_ctx_order_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "g16_ctx_last_witness_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "g16_ctx_set_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "g16_prove_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]),
     "g16_ctx_last_partials": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -1,6 +1,6 @@
 """Multi-GPU proving: one process per GPU (torch.distributed), each owning a contiguous point range of
 every MSM -- the chunking of msm.nim:107-115 lifted from CPU threads to devices.  The only exchange
-is an all-gather of one 384-byte record of partial sums per rank (msm.nim:117-119).  The blinding scalars are
+is an all-gather of one 400-byte record of partial sums per rank (msm.nim:117-119).  The blinding scalars are
 announced before the partial sums (g16_ctx_set_mask), so that the two MSM-dependent scalar multiplications of
 prover.nim:298-299 are done per rank on its own partial sums, next to its MSMs, and not after the exchange."""
 from __future__ import annotations
@@ -22,19 +22,22 @@ def shard_range(n: int, k: int, g: int):
     return lo, hi
 
 
-def shard_ranges(nvars: int, domain_size: int, k: int, g: int):
-    """g16_shard_ranges: (v_lo, v_hi, h_lo, h_hi) a ProverContext(zkey, k, g) owns -- contiguous ranges of the
-    witness-indexed arrays and of the H array.  From four ranks up the H array (with buildABC and the quotient) goes
-    to the first ranks only, which get a smaller share of the witness arrays; G16_SHARD_POLICY=uniform restores
-    shard_range() for every array."""
+PLAN_FIELDS = ("a1_lo", "a1_hi", "b1_lo", "b1_hi", "c1_lo", "c1_hi", "b2_lo", "b2_hi", "h_lo", "h_hi")
+
+
+def shard_plan(nvars: int, npubs: int, domain_size: int, k: int, g: int) -> dict:
+    """g16_shard_plan: the contiguous point range of each of the five MSMs that ProverContext(zkey, k, g) owns
+    (witness indices for A1, B1, C1, B2; domain indices for H).  The default policy places whole MSMs (or a tail /
+    head of one) per rank by a cost model; the ranks with H points run buildABC and the quotient;
+    G16_SHARD_POLICY=uniform restores shard_range() for every array."""
     import ctypes as C
-    out = (C.c_uint64 * 4)()
-    _lib.check(_lib.load().g16_shard_ranges(nvars, domain_size, k, g, out))
-    return tuple(int(x) for x in out)
+    out = (C.c_uint64 * 10)()
+    _lib.check(_lib.load().g16_shard_plan(nvars, npubs, domain_size, k, g, out))
+    return dict(zip(PLAN_FIELDS, (int(x) for x in out)))
 
 
 def gather_partials(local: "torch.Tensor", group=None) -> "torch.Tensor":   # noqa: F821
-    """All-gather of the per-rank partial-sum records (uint8[384]) -> uint8[world, 384]."""
+    """All-gather of the per-rank partial-sum records (uint8[400]) -> uint8[world, 400]."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -47,25 +50,19 @@ class ShardedProver:
     """A prover context per rank; prove() returns the full proof on every rank."""
 
     def __init__(self, zkey: ZKey, rank: int, world: int, device: Optional[int] = None,
-                 share: Optional["ShardedProver"] = None):
+                 share: Optional["ShardedProver"] = None, trusted: bool = False):
         import torch
         self.rank, self.world = rank, world
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         _lib.check(_lib.load().g16_set_device(self.device.index))
         # `share`: another slot over the same resident shard (g16_ctx_clone) for proofs in flight
-        self.ctx = share.ctx.clone() if share is not None else ProverContext(zkey, rank, world)
+        self.ctx = share.ctx.clone() if share is not None else ProverContext(zkey, rank, world, trusted=trusted)
         self.partials = torch.zeros(_lib.PARTIALS_BYTES, dtype=torch.uint8, device=self.device)
 
     def prove_raw(self, witness_ptr: int, mem_kind: int, mask: Mask, group=None):
         import torch
-        self.ctx.set_mask(mask)              # every rank: its share of s*pi_a + r*rho is computed next to its MSMs
-        self.ctx.prove_partials(witness_ptr, FORM_STD, mem_kind, self.partials.data_ptr())
-        if self.world > 1:
-            allp = gather_partials(self.partials, group)
-            torch.cuda.current_stream().synchronize()
-        else:
-            allp = self.partials.view(1, -1)
-        return self.ctx.prove_finish(allp.data_ptr(), self.world, mask)
+        self.partials_submit(witness_ptr, mem_kind, mask)
+        return self.complete(mask, group)
 
     # asynchronous halves, for overlapping consecutive proofs (one ShardedProver per proof in flight)
     def partials_submit(self, witness_ptr: int, mem_kind: int, mask: Optional[Mask] = None):
@@ -76,23 +73,32 @@ class ShardedProver:
         _lib.check(_lib.load().g16_prove_partials_submit(self.ctx._h, witness_ptr, FORM_STD, mem_kind,
                                                          self.partials.data_ptr()))
 
-    def complete(self, mask: Mask, group=None):
-        """Waits for this rank's partial sums, all-gathers them, assembles; returns the raw proof."""
-        import ctypes as C
+    def exchange_submit(self, mask: Mask, group=None):
+        """Enqueues the all-gather of the partial records and the assembly behind this rank's partial sums, ordered
+        on the device (g16_ctx_order_stream): the NCCL stream waits for the record, the context waits for the
+        all-gather -- no host synchronisation between partials_submit() and wait()."""
         import torch
         lib = _lib.load()
-        _lib.check(lib.g16_prove_partials_wait(self.ctx._h, None))
+        st = torch.cuda.current_stream(self.device)
         if self.world > 1:
-            allp = gather_partials(self.partials, group)
-            torch.cuda.current_stream().synchronize()
+            _lib.check(lib.g16_ctx_order_stream(self.ctx._h, st.cuda_stream, 0))
+            self._gathered = gather_partials(self.partials, group)       # kept alive until wait()
+            _lib.check(lib.g16_ctx_order_stream(self.ctx._h, st.cuda_stream, 1))
+            allp = self._gathered
         else:
             allp = self.partials.view(1, -1)
         from .prover import _limbs4
         _lib.check(lib.g16_prove_finish_submit(self.ctx._h, allp.data_ptr(), self.world, _limbs4(mask.r),
                                                _limbs4(mask.s)))
-        raw = _lib.ProofRaw()
-        _lib.check(lib.g16_prove_wait(self.ctx._h, C.byref(raw), None))
-        return raw
+
+    def wait(self):
+        """The proof of the last exchange_submit(); fills ctx.last_stats (this rank's phases)."""
+        return self.ctx.wait()[0]
+
+    def complete(self, mask: Mask, group=None):
+        """exchange_submit + wait: returns the raw proof."""
+        self.exchange_submit(mask, group)
+        return self.wait()
 
     def prove(self, witness: np.ndarray, mask: Mask, group=None) -> Proof:
         w = np.ascontiguousarray(witness, dtype=np.uint64).reshape(-1, 4)

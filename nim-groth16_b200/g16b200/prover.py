@@ -60,13 +60,20 @@ class ProverContext:
     """A zkey resident on one GPU (g16_ctx).  shard_index/shard_count select the point range of every MSM
     this GPU owns (msm.nim:107-115 chunking across devices)."""
 
-    def __init__(self, zkey: ZKey, shard_index: int = 0, shard_count: int = 1):
+    def __init__(self, zkey: ZKey, shard_index: int = 0, shard_count: int = 1, *, trusted: bool = False,
+                 one_shot: bool = False, devices: int = 0):
+        """`devices` = N > 0: the whole key over N devices of this process (g16_ctx_create with shard_count = -N,
+        first device `shard_index`); prove / submit / wait then work as on one GPU.  `trusted`: skip the on-curve
+        validation of the points (io.nim:228-236).  `one_shot`: no window tables (cli_main.nim:193-210 usage)."""
         lib = _lib.load()
         self.zkey = zkey
+        if devices > 0:
+            shard_count = -devices
         self.shard_index, self.shard_count = shard_index, shard_count
         v = _lib.ZkeyView()
         v.nvars, v.npubs, v.log_domain, v.flavour = zkey.nvars, zkey.npubs, zkey.logDomainSize, zkey.flavour
         v.coeff_format, v.mem_kind = COEFF_PACKED44_R2, MEM_HOST
+        v.flags = (_lib.ZKEY_TRUSTED if trusted else 0) | (_lib.ZKEY_ONE_SHOT if one_shot else 0)
         self._keep = []
 
         def ptr(a, cols):
@@ -177,6 +184,12 @@ class ProverContext:
                                                   C.byref(st)))
         self.last_stats = st.as_dict()
         return self.last_stats
+
+    def last_witness_bytes(self) -> int:
+        """Bytes of witness the last prove / partials call copied to the device(s) of this context."""
+        n = C.c_uint64()
+        _lib.check(_lib.load().g16_ctx_last_witness_bytes(self._h, C.byref(n)))
+        return int(n.value)
 
     def prove_finish(self, gathered_dev_ptr: int, count: int, mask: Mask) -> _lib.ProofRaw:
         raw = _lib.ProofRaw()

@@ -40,6 +40,7 @@ type
 
   G16ZkeyView {.bycopy.} = object       # g16_zkey_view
     nvars, npubs, logDomain, flavour, coeffFormat, memKind: uint32
+    flags, reserved0: uint32            # G16_ZKEY_TRUSTED = 1, G16_ZKEY_ONE_SHOT = 2
     ncoeffs: uint64
     coeffs: pointer
     pointsA1, pointsB1, pointsB2, pointsC1, pointsH1: pointer
@@ -74,7 +75,8 @@ proc g16_prove(ctx: G16Ctx, witness: pointer, witnessForm: cint, r, s: pointer, 
 proc g16_ctx_clone(ctx: G16Ctx, res: ptr G16Ctx): cint {.importc, cdecl.}
 proc g16_prove_submit(ctx: G16Ctx, witness: pointer, witnessForm, witnessMemKind: cint, r, s: pointer): cint {.importc, cdecl.}
 proc g16_prove_wait(ctx: G16Ctx, proof: ptr G16ProofRaw, stats: ptr G16Stats): cint {.importc, cdecl.}
-# multi-GPU hosts: one context per device over its point range, 384-byte partial records exchanged by the host
+# multi-GPU, one process: g16_ctx_create(zk, 0, -N) (or G16_NGPUS=N) and the calls above -- nothing else changes.
+# multi-GPU, one process per device: one context per rank, 400-byte partial records exchanged by the host
 proc g16_ctx_set_mask(ctx: G16Ctx, r, s: pointer): cint {.importc, cdecl.}
 proc g16_prove_partials(ctx: G16Ctx, witness: pointer, witnessForm, witnessMemKind: cint, partialsDev: pointer,
                         stats: ptr G16Stats): cint {.importc, cdecl.}

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "missing symbol " + n
         assert n in _lib.SIGNATURES, "binding missing for " + n
     assert set(_lib.SIGNATURES) == set(names)
-    assert lib.g16_version() == 1
+    assert lib.g16_version() == 2
 
 
 def test_struct_layouts_match_header():
@@ -33,8 +33,8 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.ProofRaw) == 256
     assert ctypes.sizeof(_lib.Stats) == 48
     assert ctypes.sizeof(_lib.Toxic) == 160
-    assert ctypes.sizeof(_lib.ZkeyView) == 6 * 4 + 8 + 6 * 8 + (8 + 8 + 16 + 8 + 16) * 8
-    assert _lib.PARTIALS_BYTES == 384
+    assert ctypes.sizeof(_lib.ZkeyView) == 8 * 4 + 8 + 6 * 8 + (8 + 8 + 16 + 8 + 16) * 8
+    assert _lib.PARTIALS_BYTES == 400
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="only meaningful on a box without a GPU")

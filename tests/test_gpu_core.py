@@ -253,7 +253,10 @@ def test_msm_batched_affine_tree_mode_matches():
     if os.environ.get("G16_MSM_TREE"):
         pytest.skip("already running in tree mode")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, G16_MSM_TREE="5")
+    exp_lib = os.path.join(root, "nim-groth16_b200", "libg16b200_exp.so")
+    if not os.path.exists(exp_lib):
+        pytest.skip("the experiments are not in the default library: build `make -C nim-groth16_b200 EXPERIMENTS=1`")
+    env = dict(os.environ, G16_MSM_TREE="5", G16B200_LIB=exp_lib)
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-k",
                         "msm_edge_cases or msm_resident_table_layout or msm_g2_vs_oracle_naive or reference_circuit_golden or "
                         "synthetic_circuit_closed_form or sharded_contexts_recombine",

@@ -227,7 +227,7 @@ def test_sharded_contexts_recombine_on_one_gpu(g, kat):
         ctxs = [g.ProverContext(zk, k, G) for k in range(G)]
         # masked: g16_ctx_set_mask before the partial sums (every shard folds s*A_k + r*B1_k into its c1 record)
         for masked in (False, True):
-            parts = torch.zeros((G, 384), dtype=torch.uint8, device="cuda")
+            parts = torch.zeros((G, g._lib.PARTIALS_BYTES), dtype=torch.uint8, device="cuda")
             for k, c in enumerate(ctxs):
                 if masked:
                     c.set_mask(m)
@@ -384,7 +384,7 @@ def test_full_size_proofs_pass_the_pairing_verifier(g, lg):
         assert np.array_equal(pc, prf.pi_c.reshape(-1))
         import torch
         w = np.ascontiguousarray(wit)
-        parts = torch.zeros((2, 384), dtype=torch.uint8, device="cuda")
+        parts = torch.zeros((2, g._lib.PARTIALS_BYTES), dtype=torch.uint8, device="cuda")
         for k in range(2):                                   # one shard context at a time: 2 x 2.6 GB of tables
             c = g.ProverContext(zk, k, 2)
             c.prove_partials(w.ctypes.data, e.FORM_STD, 0, parts[k].data_ptr())

@@ -119,3 +119,56 @@ def test_file_round_trips(kat):
     assert o.write_zkey_bytes(zk).hex() == kat["snarkjs"]["zkey_hex"]
     assert o.parse_wtns_bytes(bytes.fromhex(kat["wtns_hex"])) == o.REFERENCE_TEST_WITNESS
     assert zk.nvars == 8 and zk.npubs == 2 and zk.domainSize == 8 and len(zk.coeffs) == 7
+
+
+# ------------------------------------------------------------------------------------------------
+# Third-party BN254 (alt_bn128) vectors: values the builder did not compute.  They are the published test
+# vectors of the Ethereum precompiles (EIP-196 ecAdd / ecMul cases "chfast1" of the go-ethereum / ethereum-tests
+# suites) and the EIP-197 G2 generator; they pin the oracle's curve layer (curves.nim:136-154 addG1,
+# :182-196 `**`) against an independent implementation.
+# ------------------------------------------------------------------------------------------------
+EIP196_TWO_G1 = (0x030644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd3,
+                 0x15ed738c0e0a7c92e7845f96b2ae9c0a68a6a449e3538fc7ff3ebf7a5a18a2c4)
+EIP196_ADD_CHFAST1 = (
+    (0x18b18acfb4c2c30276db5411368e7185b311dd124691610c5d3b74034e093dc9,
+     0x063c909c4720840cb5134cb9f59fa749755796819658d32efc0d288198f37266),
+    (0x07c2b7f58a84bd6145f00c9c2bc0bb1a187f20ff2c92963a88019e7c6a014eed,
+     0x06614e20c147e940f2d70da3f74c9a17df361706a4485c742bd6788478fa17d7),
+    (0x2243525c5efd4b9c3d3c45ac0ca3fe4dd85e830a4ce6b65fa1eeaee202839703,
+     0x301d1d33be6da8e509df21cc35964723180eed7532537db9ae5e7d48f195c915))
+EIP196_MUL_CHFAST1 = (
+    (0x2bd3e6d0f3b142924f5ca7b49ce5b9d54c4703d7ae5648e61d02268b1a0a9fb7,
+     0x21611ce0a6af85915e2f1d70300909ce2e49dfad4a4619c8390cae66cefdb204),
+    0x00000000000000000000000000000000000000000000000011138ce750fa15c2,
+    (0x070a8d6a982153cae4be29d434e8faef8a47b274a053f5a4ee2a6c9c13c31e5c,
+     0x031b8ce914eba3a9ffb989f9cdd5b0f01943074bf4f0f315690ec3cec6981afc))
+EIP197_G2 = ((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+              11559732032986387107991004021392285783925812861821192530917403151452391805634),
+             (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+              4082367875863433681332203403145435568316851327593401208105741076214120093531))
+
+
+def test_third_party_bn254_vectors_g1():
+    assert o.g1_add(o.GEN1, o.GEN1) == EIP196_TWO_G1
+    assert o.g1_mul(2, o.GEN1) == EIP196_TWO_G1
+    assert o.msm_naive_g1([2], [o.GEN1]) == EIP196_TWO_G1
+    a, b, c = EIP196_ADD_CHFAST1
+    assert o.is_on_curve_g1(a) and o.is_on_curve_g1(b) and o.g1_add(a, b) == c and o.g1_add(b, a) == c
+    p, k, q = EIP196_MUL_CHFAST1
+    assert o.is_on_curve_g1(p) and o.g1_mul(k, p) == q
+    assert o.msm_naive_g1([k, 1], [p, a]) == o.g1_add(q, a)
+    assert o.g1_mul(o.R, p) == o.INF_G1 and o.g1_mul(o.R - 1, o.GEN1) == (1, o.P - 2)
+
+
+def test_third_party_bn254_vectors_g2_and_pairing():
+    """The EIP-197 generator of G2 (not the generator curves.nim:115-121 uses) lies on the twist and in the
+    order-r subgroup under the oracle's G2 arithmetic, and pairs bilinearly with the EIP-196 points."""
+    import bn254_pairing as bp
+    assert o.is_on_curve_g2(EIP197_G2)
+    assert o.g2_mul(o.R, EIP197_G2) == o.INF_G2
+    assert o.g2_add(o.g2_mul(5, EIP197_G2), o.g2_mul(o.R - 5, EIP197_G2)) == o.INF_G2
+    # the ecPairing identity of EIP-197: e(P, Q) * e(-P, Q) = 1, and e(2P, Q) = e(P, 2Q) with the published 2P
+    e1 = bp.pairing(o.GEN1, EIP197_G2)
+    assert not (e1 == bp.F12.one())
+    assert e1 * bp.pairing(o.g1_neg(o.GEN1), EIP197_G2) == bp.F12.one()
+    assert bp.pairing(EIP196_TWO_G1, EIP197_G2) == bp.pairing(o.GEN1, o.g2_mul(2, EIP197_G2)) == e1 * e1

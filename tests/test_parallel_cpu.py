@@ -28,7 +28,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from g16b200.parallel import gather_partials
-    local = torch.full((384,), rank + 1, dtype=torch.uint8)
+    local = torch.full((400,), rank + 1, dtype=torch.uint8)
     local[0] = 7 * (rank + 1)
     out = gather_partials(local)
     q.put((rank, out.tolist()))
@@ -54,7 +54,7 @@ def test_gather_partials_world2_gloo():
     for rank in (0, 1):
         rows = res[rank]
         assert len(rows) == 2 and rows[0][0] == 7 and rows[1][0] == 14
-        assert rows[0][1:] == [1] * 383 and rows[1][1:] == [2] * 383
+        assert rows[0][1:] == [1] * 399 and rows[1][1:] == [2] * 399
 
 
 def test_sharded_partial_sums_recombine_in_the_oracle():
@@ -74,37 +74,72 @@ def test_sharded_partial_sums_recombine_in_the_oracle():
         assert acc == whole
 
 
-def test_library_shard_ranges_partition_every_array():
-    """g16_shard_ranges (host arithmetic of the C library, no GPU): for every world size the witness ranges and
-    the H ranges are contiguous, ordered, disjoint and cover [0, nvars) / [0, n); the ranks without H points are
-    the ones that skip buildABC and the quotient; below four ranks the split is the reference's chunking."""
-    from g16b200.parallel import shard_range, shard_ranges
-    for nvars, n in ((1, 2), (5, 8), (1000, 1024), ((1 << 20) - 2 + 2, 1 << 20), ((1 << 22) + 17, 1 << 23)):
+def _plan_pieces(nvars, npubs, n, g):
+    from g16b200.parallel import shard_plan
+    return [shard_plan(nvars, npubs, n, k, g) for k in range(g)]
+
+
+def test_library_shard_plan_partitions_every_array(monkeypatch):
+    """g16_shard_plan (host arithmetic of the C library, no GPU): for every world size and policy each of the five
+    arrays is cut into contiguous, ordered, disjoint ranges that cover it exactly once (so the partial sums add up
+    to the whole MSM, msm.nim:117-119); at least one rank owns H points (and with them buildABC + the quotient);
+    one rank reproduces the whole job; the uniform policy is the reference's chunking of every array."""
+    from g16b200.parallel import shard_range
+    import subprocess, sys, json, os
+    sizes = ((1, 0, 2), (5, 1, 8), (1000, 3, 1024), (1 << 20, 1, 1 << 20), ((1 << 22) + 17, 2, 1 << 23))
+    for nvars, npubs, n in sizes:
         for g in (1, 2, 3, 4, 5, 8, 16):
-            va = ha = 0
-            h_ranks = 0
-            for k in range(g):
-                v_lo, v_hi, h_lo, h_hi = shard_ranges(nvars, n, k, g)
-                assert v_lo == va and v_hi >= v_lo
-                va = v_hi
-                if h_hi > h_lo:
-                    assert h_lo == ha
-                    ha = h_hi
-                    h_ranks += 1
-                    assert g < 4 or k < max(1, g // 4)      # from 4 ranks up the H group is among the first ranks
-            assert va == nvars and ha == n and h_ranks >= 1
-            if g < 4:
-                for k in range(g):
-                    assert shard_ranges(nvars, n, k, g) == shard_range(nvars, k, g) + shard_range(n, k, g)
+            plans = _plan_pieces(nvars, npubs, n, g)
+            for name, total in (("a1", nvars), ("b1", nvars), ("c1", nvars), ("b2", nvars), ("h", n)):
+                at = 0
+                for p in plans:
+                    lo, hi = p[name + "_lo"], p[name + "_hi"]
+                    if hi > lo:
+                        assert lo == at, (name, g, plans)
+                        at = hi
+                assert at == total, (name, g, plans)
+            assert sum(1 for p in plans if p["h_hi"] > p["h_lo"]) >= 1
+            if g == 1:
+                p = plans[0]
+                assert all(p[k + "_lo"] == 0 for k in ("a1", "b1", "c1", "b2", "h"))
+    # at the benchmark sizes no rank owns pieces of more than three witness arrays besides whole arrays, and the
+    # ranks without H points do not need the whole witness
+    for lg in (20, 22):
+        for g in (2, 4, 8):
+            plans = _plan_pieces(1 << lg, 1, 1 << lg, g)
+            assert any(p["h_hi"] == p["h_lo"] for p in plans) or g == 2
+    # the policy is read once per process: check the other two in child processes
+    code = ("import sys, json; sys.path.insert(0, %r); from g16b200.parallel import shard_plan; "
+            "print(json.dumps([shard_plan(1000, 3, 1024, k, 4) for k in range(4)]))"
+            % os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nim-groth16_b200"))
+    for policy in ("uniform", "g2own"):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, G16_SHARD_POLICY=policy),
+                             capture_output=True, text=True, check=True).stdout
+        plans = json.loads(out)
+        for name, total in (("a1", 1000), ("b1", 1000), ("c1", 1000), ("b2", 1000), ("h", 1024)):
+            at = 0
+            for p in plans:
+                if p[name + "_hi"] > p[name + "_lo"]:
+                    assert p[name + "_lo"] == at
+                    at = p[name + "_hi"]
+            assert at == total
+        if policy == "uniform":
+            for k, p in enumerate(plans):
+                assert (p["a1_lo"], p["a1_hi"]) == shard_range(1000, k, 4) == (p["b2_lo"], p["b2_hi"])
+                assert (p["h_lo"], p["h_hi"]) == shard_range(1024, k, 4)
+        else:
+            assert (plans[3]["b2_lo"], plans[3]["b2_hi"]) == (0, 1000)
+            assert all(p["b2_hi"] == p["b2_lo"] for p in plans[:3])
+            assert plans[3]["a1_hi"] == plans[3]["a1_lo"] and plans[3]["h_hi"] == plans[3]["h_lo"]
 
 
 def test_masked_shard_records_recombine_in_the_oracle(kat):
     """The algebra of the multi-GPU path (g16_ctx_set_mask, k_shard_early, k_assemble_final_masked of prover.cu)
     restated with the oracle's group law on the reference's test circuit: every rank ships
-    c1' = C_k + s*A_k + r*B1_k over the ranges of g16_shard_ranges, and
+    c1' = C_k + s*A_k + r*B1_k over the ranges of g16_shard_plan (inf for an MSM it owns no points of), and
         pi_c = sum c1'_k + sum H_k + s*alpha1 + r*beta1 + (r s)*delta1,   pi_a, pi_b from the plain sums
-    reproduce generateProofWithMask (prover.nim:278-304) for the uniform split (2 ranks) and the H group (4, 8)."""
-    from g16b200.parallel import shard_ranges
+    reproduce generateProofWithMask (prover.nim:278-304) for 2, 3, 4 and 8 ranks."""
+    from g16b200.parallel import shard_plan
     zk = o.parse_zkey_bytes(bytes.fromhex(kat["snarkjs"]["zkey_hex"]))
     w = [int(v, 16) if isinstance(v, str) else int(v) for v in kat["witness"]]
     r, s = int(kat["mask"]["r"], 16), int(kat["mask"]["s"], 16)
@@ -112,17 +147,17 @@ def test_masked_shard_records_recombine_in_the_oracle(kat):
     want = o.generate_proof_with_mask(zk, w, r, s, intermediates=inter)
     qs = inter["qs"]
     first = zk.npubs + 1
-    for g in (2, 4, 8):
+    for g in (2, 3, 4, 8):
         A = B1 = C = H = o.INF_G1
         B2 = o.INF_G2
         for k in range(g):
-            v_lo, v_hi, h_lo, h_hi = shard_ranges(zk.nvars, zk.domainSize, k, g)
-            a_k = o.msm_naive_g1(w[v_lo:v_hi], zk.pointsA1[v_lo:v_hi])
-            b1_k = o.msm_naive_g1(w[v_lo:v_hi], zk.pointsB1[v_lo:v_hi])
-            b2_k = o.msm_naive_g2(w[v_lo:v_hi], zk.pointsB2[v_lo:v_hi])
-            c_lo, c_hi = max(v_lo, first), max(v_hi, first)              # C1[j - npubs - 1] multiplies witness[j]
+            p = shard_plan(zk.nvars, zk.npubs, zk.domainSize, k, g)
+            a_k = o.msm_naive_g1(w[p["a1_lo"]:p["a1_hi"]], zk.pointsA1[p["a1_lo"]:p["a1_hi"]])
+            b1_k = o.msm_naive_g1(w[p["b1_lo"]:p["b1_hi"]], zk.pointsB1[p["b1_lo"]:p["b1_hi"]])
+            b2_k = o.msm_naive_g2(w[p["b2_lo"]:p["b2_hi"]], zk.pointsB2[p["b2_lo"]:p["b2_hi"]])
+            c_lo, c_hi = max(p["c1_lo"], first), max(p["c1_hi"], first)      # C1[j - npubs - 1] multiplies witness[j]
             c_k = o.msm_naive_g1(w[c_lo:c_hi], zk.pointsC1[c_lo - first:c_hi - first])
-            h_k = o.msm_naive_g1(qs[h_lo:h_hi], zk.pointsH1[h_lo:h_hi])
+            h_k = o.msm_naive_g1(qs[p["h_lo"]:p["h_hi"]], zk.pointsH1[p["h_lo"]:p["h_hi"]])
             c1p = o.g1_add(o.g1_add(c_k, o.g1_mul(s, a_k)), o.g1_mul(r, b1_k))   # the record's c1 field
             A, B1, B2 = o.g1_add(A, a_k), o.g1_add(B1, b1_k), o.g2_add(B2, b2_k)
             C, H = o.g1_add(C, c1p), o.g1_add(H, h_k)

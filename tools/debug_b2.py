@@ -17,7 +17,7 @@ for neqs in (1000, 5000):
     r, s = o.Rng(seed+10).fr(), o.Rng(seed+11).fr()
     wantB = o.g2_mul((tox_o.beta + s * tox_o.delta + mB) % o.R, o.GEN2)
     wantM = o.g2_mul(mB, o.GEN2)
-    parts = torch.zeros(384, dtype=torch.uint8, device="cuda")
+    parts = torch.zeros(400, dtype=torch.uint8, device="cuda")
     bad = 0
     for rep in range(60):
         ctx = g.ProverContext(zk)

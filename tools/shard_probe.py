@@ -10,7 +10,7 @@ log_n = int(sys.argv[1]); G = int(sys.argv[2])
 lib = _lib.load()
 zk, wit, _ = bench.make_fixture(g, log_n)
 w = torch.from_numpy(np.ascontiguousarray(wit).view(np.int64).copy()).to("cuda")
-parts = torch.zeros(384, dtype=torch.uint8, device="cuda")
+parts = torch.zeros(400, dtype=torch.uint8, device="cuda")
 mask = g.Mask(bench.MASK_R, bench.MASK_S)
 for shards in ([G] if G else [1, 2, 4, 8]):
     worst = 0.0
