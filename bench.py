@@ -498,7 +498,7 @@ def extra_lines(args, g, lib, zk, w_np, ctxs, mask, torch):
     # HOST zkey arrays (validated upload) + one proof + destroy, wall clock; one-shot layout vs resident tables
     for name, one_shot in (("cold_e2e", True), ("cold_e2e_tables", False)):
         ts = []
-        for _ in range(3):
+        for _ in range(4):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             c = g.ProverContext(zk, one_shot=one_shot)
@@ -510,9 +510,12 @@ def extra_lines(args, g, lib, zk, w_np, ctxs, mask, torch):
             ts.append((t3 - t0, t1 - t0, t2 - t1))
         best = min(ts)
         res[name] = {"ms": best[0] * 1e3, "create_ms": best[1] * 1e3, "prove_ms": best[2] * 1e3, "unit": "ms",
+                     "first_call_ms": ts[0][0] * 1e3,
                      "layout": "plain points (G16_ZKEY_ONE_SHOT)" if one_shot else "resident window tables",
                      "point_validation": "on", "witness": "pageable host memory",
-                     "what": "g16_ctx_create from host zkey arrays + g16_prove + g16_ctx_destroy, wall clock, best of 3"}
+                     "what": "g16_ctx_create from host zkey arrays + g16_prove + g16_ctx_destroy, wall clock, best of 4 in one "
+                             "process (device memory of a destroyed context stays in the library's pool); first_call_ms "
+                             "is the first of them"}
     warm = 1e3 / res_value(ctxs, w_np, mask, E, 3)
     d_create = res["cold_e2e_tables"]["create_ms"] - res["cold_e2e"]["create_ms"]
     d_prove = res["cold_e2e"]["prove_ms"] - warm
@@ -540,8 +543,9 @@ def extra_lines(args, g, lib, zk, w_np, ctxs, mask, torch):
     for _ in range(args.steps):
         c.prove_ptr(wsp.data_ptr(), mask, E.FORM_STD)
     dts = (time.perf_counter() - t0) / args.steps
-    t0 = time.perf_counter()
     wp = torch.from_numpy(w_np.view(np.int64).copy()).pin_memory()
+    c.prove_ptr(wp.data_ptr(), mask, E.FORM_STD)
+    t0 = time.perf_counter()
     for _ in range(args.steps):
         c.prove_ptr(wp.data_ptr(), mask, E.FORM_STD)
     dtu = (time.perf_counter() - t0) / args.steps

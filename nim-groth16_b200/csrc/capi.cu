@@ -25,6 +25,25 @@ const char* get_last_error() { return t_last_error.c_str(); }
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// per-device internal stream of the stream-ordered allocator (DevBuf); the pool keeps freed memory cached
+cudaStream_t pool_stream() {
+  static std::mutex mu;
+  static cudaStream_t streams[64] = {nullptr};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!streams[dev]) {
+    G16_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
+    cudaMemPool_t pool = nullptr;
+    G16_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = ~0ull;
+    if (const char* e = getenv("G16_POOL_KEEP_MB")) keep = (uint64_t)atoll(e) << 20;   // 0: give memory back on free
+    G16_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  return streams[dev];
+}
+
 void fake_setup(const g16_r1cs_view& r, const g16_toxic& toxic, uint32_t* log_domain_out, g16_setup_out& out);
 template <class F>
 void fixed_base_mul(const Fr* scalars_dev, size_t n, Affine<F>* out_dev, cudaStream_t stream);

@@ -38,15 +38,34 @@ void count_launch();   // capi.cu
   } while (0)
 
 // RAII device allocation (grow-only reuse through ensure()).
+//
+// Memory comes from the device's stream-ordered pool (cudaMallocAsync) with the release threshold lifted, so what a
+// destroyed context frees stays cached in the process: a host that creates a context per proof -- the shape of
+// the reference's generateProofWithMask(zkey, witness), cli_main.nim:193-210 -- pays for cudaMalloc / cudaFree of
+// gigabytes once, not per call.  Semantics stay those of cudaMalloc / cudaFree: an allocation is usable on any
+// stream when ensure() returns, and release() waits for the device first (as cudaFree does implicitly).
+cudaStream_t pool_stream();            // capi.cu: per-device internal stream; configures the pool on first use
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  int dev = -1;
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      int cur = 0;
+      cudaGetDevice(&cur);
+      if (dev >= 0 && dev != cur) cudaSetDevice(dev);
+      cudaDeviceSynchronize();
+      cudaStream_t s = pool_stream();
+      if (cudaFreeAsync(p, s) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(p);
+      }
+      if (dev >= 0 && dev != cur) cudaSetDevice(cur);
+    }
     p = nullptr;
     bytes = 0;
   }
@@ -54,7 +73,10 @@ struct DevBuf {
     if (n <= bytes) return;
     release();
     if (n == 0) return;
-    G16_CUDA(cudaMalloc(&p, n));
+    G16_CUDA(cudaGetDevice(&dev));
+    cudaStream_t s = pool_stream();
+    G16_CUDA(cudaMallocAsync(&p, n, s));
+    G16_CUDA(cudaStreamSynchronize(s));
     bytes = n;
   }
   template <class T>

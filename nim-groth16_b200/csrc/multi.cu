@@ -29,6 +29,19 @@ MultiProver::MultiProver(const g16_zkey_view& zk, const std::vector<int>& device
       if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) G16_CUDA(e);
       cudaGetLastError();
     }
+    // DevBuf memory comes from the stream-ordered pools: make them peer-accessible as well (NVLink copies of the
+    // records and of a device-resident witness instead of copies staged through the host)
+    for (int a = 0; a < 2; a++) {
+      const int owner = a ? dev_[0] : dev_[k], peer = a ? dev_[k] : dev_[0];
+      cudaMemPool_t pool = nullptr;
+      if (cudaDeviceGetDefaultMemPool(&pool, owner) != cudaSuccess) continue;
+      cudaMemAccessDesc d;
+      memset(&d, 0, sizeof(d));
+      d.location.type = cudaMemLocationTypeDevice;
+      d.location.id = peer;
+      d.flags = cudaMemAccessFlagsProtReadWrite;
+      if (cudaMemPoolSetAccess(pool, &d, 1) != cudaSuccess) cudaGetLastError();
+    }
   }
   for (int k = 0; k < G; k++) {
     DeviceGuard g(dev_[k]);
