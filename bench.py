@@ -432,15 +432,24 @@ def run_ours(args):
     for c in ctxs:
         c.close()
     if dist is not None:
+        _lib.check(lib.g16_release_cached_memory())    # every rank gives its cached device memory back first
+        torch.cuda.synchronize()
         dist.barrier()
         # rank 0 alone, every other rank idle: the SAME N GPUs driven by one process through the in-library
         # multi-device context (g16_ctx_create with shard_count = -N) -- the path a Nim caller of
         # generateProofWithMask gets; peer copies instead of NCCL
-        if rank == 0 and not args.no_micro:
-            try:
-                out["in_library_multi_gpu"] = inlib_line(args, g, lib, zk, w_pinned, w_dev, mask, raw, world, torch)
-            except Exception as ex:
-                out["in_library_multi_gpu"] = {"failed": repr(ex)}
+        # (the other ranks wait on the rendezvous store, not in an NCCL barrier whose kernel would spin on their GPUs)
+        from datetime import timedelta
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            if not args.no_micro:
+                try:
+                    out["in_library_multi_gpu"] = inlib_line(args, g, lib, zk, w_pinned, w_dev, mask, raw, world, torch)
+                except Exception as ex:
+                    out["in_library_multi_gpu"] = {"failed": repr(ex)}
+            store.set("g16_inlib_done", "1")
+        else:
+            store.wait(["g16_inlib_done"], timedelta(seconds=600))
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:

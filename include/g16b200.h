@@ -60,6 +60,10 @@ int g16_device_count(int* count);
  * staged pageable copies.  Optional; undo with g16_host_unregister before unmapping. */
 int g16_host_register(const void* ptr, size_t bytes);
 int g16_host_unregister(const void* ptr);
+/* Device memory freed by destroyed contexts stays cached in the library's stream-ordered pools (a context per proof
+ * then costs no cudaMalloc / cudaFree); this returns the cached memory of every device to the driver.  Environment
+ * G16_POOL_KEEP_MB=<n> bounds the cache instead (0 = keep nothing). */
+int g16_release_cached_memory(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Fine-grained level: one call per reference proc, host buffers in and out.

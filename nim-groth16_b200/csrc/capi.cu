@@ -26,9 +26,11 @@ static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // per-device internal stream of the stream-ordered allocator (DevBuf); the pool keeps freed memory cached
+static std::mutex g_pool_mu;
+static cudaStream_t g_pool_streams[64] = {nullptr};
 cudaStream_t pool_stream() {
-  static std::mutex mu;
-  static cudaStream_t streams[64] = {nullptr};
+  std::mutex& mu = g_pool_mu;
+  cudaStream_t* streams = g_pool_streams;
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lock(mu);
@@ -42,6 +44,15 @@ cudaStream_t pool_stream() {
     G16_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
   return streams[dev];
+}
+
+void pool_trim() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaMemPool_t pool = nullptr;
+  cudaDeviceSynchronize();
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  cudaGetLastError();
 }
 
 void fake_setup(const g16_r1cs_view& r, const g16_toxic& toxic, uint32_t* log_domain_out, g16_setup_out& out);
@@ -203,6 +214,20 @@ int g16_device_count(int* count) {
   });
 }
 
+int g16_release_cached_memory(void) {
+  return guard([&] {
+    int n = 0, cur = 0;
+    G16_CUDA(cudaGetDeviceCount(&n));
+    cudaGetDevice(&cur);
+    ntt_release_tables();
+    for (int d = 0; d < n && d < 64; d++) {
+      if (!g_pool_streams[d]) continue;              // only devices this library has allocated on
+      cudaSetDevice(d);
+      pool_trim();
+    }
+    cudaSetDevice(cur);
+  });
+}
 int g16_host_register(const void* ptr, size_t bytes) {
   return guard([&] {
     G16_REQUIRE(ptr != nullptr && bytes > 0, "null range");

@@ -45,6 +45,7 @@ void count_launch();   // capi.cu
 // gigabytes once, not per call.  Semantics stay those of cudaMalloc / cudaFree: an allocation is usable on any
 // stream when ensure() returns, and release() waits for the device first (as cudaFree does implicitly).
 cudaStream_t pool_stream();            // capi.cu: per-device internal stream; configures the pool on first use
+void pool_trim();                      // capi.cu: returns the cached memory of the current device's pool to the driver
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -75,8 +76,24 @@ struct DevBuf {
     if (n == 0) return;
     G16_CUDA(cudaGetDevice(&dev));
     cudaStream_t s = pool_stream();
-    G16_CUDA(cudaMallocAsync(&p, n, s));
-    G16_CUDA(cudaStreamSynchronize(s));
+    cudaError_t e = cudaMallocAsync(&p, n, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+      // the pool could not serve the request (fragmented cache, or memory held by other processes): give the cached
+      // memory back to the driver and take a plain allocation
+      cudaGetLastError();
+      p = nullptr;
+      pool_trim();
+      e = cudaMalloc(&p, n);
+      if (e != cudaSuccess) {
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        cudaGetLastError();
+        throw Error(2, std::string("device allocation of ") + std::to_string(n) + " bytes failed on device " +
+                           std::to_string(dev) + " (" + cudaGetErrorString(e) + "; free " + std::to_string(fr) + " of " +
+                           std::to_string(tot) + ")");
+      }
+    }
     bytes = n;
   }
   template <class T>

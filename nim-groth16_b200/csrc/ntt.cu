@@ -10,6 +10,7 @@
 // decimation-in-time (bit-reversed in, natural out), so shiftEvalDomain needs no permutation pass:
 // the coset factor eta^i / n is applied, indexed by bit-reversal, in the last inverse pass.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -129,7 +130,7 @@ void ntt_release_tables() {
 // ---------------------------------------------------------------------------------------
 // the pass kernel
 // ---------------------------------------------------------------------------------------
-enum { SC_NONE = 0, SC_CONST = 1, SC_TABLE_BITREV = 2 };
+enum { SC_NONE = 0, SC_CONST = 1, SC_TABLE_BITREV = 2, SC_TABLE = 3 };
 
 struct NttPassArgs {
   const Fr* src;        // batch b reads src + b * src_stride
@@ -140,6 +141,7 @@ struct NttPassArgs {
   int log_n, t_lo, k, logC;
   int scale_mode;
   int bitrev_store;     // store element g at dst[bitrev(g)]
+  int bitrev_load;      // load element g from src[bitrev(g)]  (gather: natural-order input of a DIT transform)
 };
 
 #ifndef G16_NTT_THREADS
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(NTT_THREADS, G16_NTT_MINB) k_ntt_pass(NttPassA
 
   for (uint32_t p = threadIdx.x; p < E; p += NTT_THREADS) {
     uint32_t g = ntt_global_index(tile, p, a.t_lo, a.k, a.logC);
-    sm_put(sm, E, p, ld_fr(src + g));
+    sm_put(sm, E, p, ld_fr(src + (a.bitrev_load ? (__brev(g) >> (32 - a.log_n)) : g)));
   }
   __syncthreads();
 
@@ -226,7 +228,133 @@ __global__ void __launch_bounds__(NTT_THREADS, G16_NTT_MINB) k_ntt_pass(NttPassA
     uint32_t gr = __brev(g) >> (32 - a.log_n);
     if (a.scale_mode == SC_CONST) x = fmul(x, ldg_fr(a.scale));
     else if (a.scale_mode == SC_TABLE_BITREV) x = fmul(x, ldg_fr(a.scale + gr));
+    else if (a.scale_mode == SC_TABLE) x = fmul(x, ldg_fr(a.scale + g));
     st_fr(dst + (a.bitrev_store ? gr : g), x);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// the pass kernel for full tiles (k + logC == 11): radix-8 groups in registers
+//
+// A thread holds 8 elements (64 registers) and runs up to three butterfly stages on them -- 12 butterflies, 12
+// twiddle multiplications, no shared memory and no barrier -- then the CTA regroups through shared memory for the
+// next three index bits.  An 11-bit pass is 3+3+3+2 stages with three exchanges where the radix-2 kernel above has
+// eleven shared-memory round trips and barriers; shared memory moves 16-byte halves (LDS.128 / STS.128, XOR-swizzled
+// so that a quarter-warp hits eight distinct bank groups).  Global stores are sector-complete: the two lanes of a
+// pair swap halves by shuffle so that one store instruction writes the 32 bytes of an element contiguously (no
+// partial-sector writes, which is what amplified the DRAM writes of the radix-2 kernel 3-5x).
+// 256 threads x 8 elements = one 2048-element tile, 2 CTAs per SM: 512 tiles of a 2^20 transform on 296 slots.
+// ---------------------------------------------------------------------------------------
+constexpr int NTT8_THREADS = 256;
+
+// tile position of element j (0..7) of thread t in a group that owns position bits [b, b + r): the low r bits of
+// j are the group's stage bits, the other 3 - r bits select one of 2^(3-r) independent sets
+__device__ __forceinline__ uint32_t ntt8_pos(uint32_t t, uint32_t j, int b, int r) {
+  const uint32_t jlow = j & ((1u << r) - 1u), jset = j >> r;
+  const uint32_t u = (jset << 8) | t;
+  return ((u >> b) << (b + r)) | (jlow << b) | (u & ((1u << b) - 1u));
+}
+__device__ __forceinline__ uint32_t ntt8_phys(uint32_t p) { return p ^ ((p >> 3) & 7u); }
+
+__device__ __forceinline__ uint4 shfl_xor4(uint4 v, int m) {
+  v.x = __shfl_xor_sync(0xffffffffu, v.x, m);
+  v.y = __shfl_xor_sync(0xffffffffu, v.y, m);
+  v.z = __shfl_xor_sync(0xffffffffu, v.z, m);
+  v.w = __shfl_xor_sync(0xffffffffu, v.w, m);
+  return v;
+}
+
+template <bool DIF>
+__global__ void __launch_bounds__(NTT8_THREADS, 2) k_ntt_pass8(NttPassArgs a) {
+  extern __shared__ uint4 sm4[];
+  uint4* const sm_lo = sm4;
+  uint4* const sm_hi = sm4 + (1u << NTT_TILE_LOG);
+  const uint32_t t = threadIdx.x, tile = blockIdx.x;
+  const Fr* src = a.src + (size_t)blockIdx.y * a.src_stride;
+  Fr* dst = a.dst + (size_t)blockIdx.y * a.dst_stride;
+  const int ng = (a.k + 2) / 3;
+  const int rlast = a.k - 3 * (ng - 1);
+  Fr x[8];
+  uint32_t g[8];
+
+#pragma unroll 1
+  for (int gi = 0; gi < ng; gi++) {
+    // DIF walks the stage bits from the top, DIT from the bottom; the group with fewer than 3 bits comes last
+    const int r = gi < ng - 1 ? 3 : rlast;
+    const int b = DIF ? (gi < ng - 1 ? a.logC + a.k - 3 * (gi + 1) : a.logC) : a.logC + 3 * gi;
+    if (gi == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        g[j] = ntt_global_index(tile, ntt8_pos(t, j, b, r), a.t_lo, a.k, a.logC);
+        x[j] = ld_fr(src + (a.bitrev_load ? (__brev(g[j]) >> (32 - a.log_n)) : g[j]));
+      }
+    } else {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t p = ntt8_pos(t, j, b, r), P = ntt8_phys(p);
+        g[j] = ntt_global_index(tile, p, a.t_lo, a.k, a.logC);
+        const uint4 lo = sm_lo[P], hi = sm_hi[P];
+        x[j].v[0] = lo.x; x[j].v[1] = lo.y; x[j].v[2] = lo.z; x[j].v[3] = lo.w;
+        x[j].v[4] = hi.x; x[j].v[5] = hi.y; x[j].v[6] = hi.z; x[j].v[7] = hi.w;
+      }
+    }
+    const int tg0 = a.t_lo + (b - a.logC);                // global index bit of the group's stage 0
+#pragma unroll
+    for (int qq = 0; qq < 3; qq++) {
+      const int q = DIF ? 2 - qq : qq;
+      if (q < r) {
+        const int tg = tg0 + q;
+        const uint32_t mask = (1u << tg) - 1u;
+        const int sh = a.log_n - 1 - tg;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (j & (1 << q)) continue;
+          Fr& u = x[j];
+          Fr& v = x[j | (1 << q)];
+          if (DIF) {
+            Fr d = fsub(u, v);
+            if (tg != 0) d = fmul(d, ldg_fr(a.tw + ((g[j] & mask) << sh)));
+            u = fadd(u, v);
+            v = d;
+          } else {
+            Fr w = v;
+            if (tg != 0) w = fmul(w, ldg_fr(a.tw + ((g[j] & mask) << sh)));
+            v = fsub(u, w);
+            u = fadd(u, w);
+          }
+        }
+      }
+    }
+    if (gi < ng - 1) {
+      if (gi > 0) __syncthreads();                        // everyone has read the previous exchange
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t P = ntt8_phys(ntt8_pos(t, j, b, r));
+        sm_lo[P] = make_uint4(x[j].v[0], x[j].v[1], x[j].v[2], x[j].v[3]);
+        sm_hi[P] = make_uint4(x[j].v[4], x[j].v[5], x[j].v[6], x[j].v[7]);
+      }
+    }
+  }
+
+  const bool odd = threadIdx.x & 1u;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    Fr v = x[j];
+    const uint32_t gr = __brev(g[j]) >> (32 - a.log_n);
+    if (a.scale_mode == SC_CONST) v = fmul(v, ldg_fr(a.scale));
+    else if (a.scale_mode == SC_TABLE_BITREV) v = fmul(v, ldg_fr(a.scale + gr));
+    else if (a.scale_mode == SC_TABLE) v = fmul(v, ldg_fr(a.scale + g[j]));
+    const uint32_t di = a.bitrev_store ? gr : g[j];
+    const uint4 lo = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]), hi = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+    // lane pair (even, odd): the even lane hands over its high half and takes the odd lane's low half, so that
+    // store 1 writes the even lane's element and store 2 the odd lane's element as 32 contiguous bytes
+    const uint4 got = shfl_xor4(odd ? lo : hi, 1);
+    const uint32_t dj = __shfl_xor_sync(0xffffffffu, di, 1);
+    uint4* const p1 = reinterpret_cast<uint4*>(dst + (odd ? dj : di)) + (odd ? 1 : 0);
+    uint4* const p2 = reinterpret_cast<uint4*>(dst + (odd ? di : dj)) + (odd ? 1 : 0);
+    *p1 = odd ? got : lo;
+    *p2 = odd ? hi : got;
   }
 }
 
@@ -239,14 +367,26 @@ static void launch_pass(bool dif, const NttPassArgs& a, int batch, cudaStream_t 
   if (!(attr_devices.load(std::memory_order_relaxed) & bit)) {
     G16_CUDA(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     G16_CUDA(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    G16_CUDA(cudaFuncSetAttribute(k_ntt_pass8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    G16_CUDA(cudaFuncSetAttribute(k_ntt_pass8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_devices.fetch_or(bit, std::memory_order_relaxed);
   }
   size_t E = (size_t)1 << (a.k + a.logC);
   size_t tiles = ((size_t)1 << a.log_n) / E;
   dim3 grid((unsigned)tiles, (unsigned)batch);
   size_t smem = E * sizeof(Fr);
-  if (dif) k_ntt_pass<true><<<grid, NTT_THREADS, smem, stream>>>(a);
-  else k_ntt_pass<false><<<grid, NTT_THREADS, smem, stream>>>(a);
+  static int use8 = -1;
+  if (use8 < 0) {
+    const char* e = getenv("G16_NTT_RADIX2");           // A/B knob: force the radix-2 shared-memory kernel
+    use8 = (e && e[0] == '1') ? 0 : 1;
+  }
+  if (use8 && a.k + a.logC == NTT_TILE_LOG) {
+    if (dif) k_ntt_pass8<true><<<grid, NTT8_THREADS, smem, stream>>>(a);
+    else k_ntt_pass8<false><<<grid, NTT8_THREADS, smem, stream>>>(a);
+  } else {
+    if (dif) k_ntt_pass<true><<<grid, NTT_THREADS, smem, stream>>>(a);
+    else k_ntt_pass<false><<<grid, NTT_THREADS, smem, stream>>>(a);
+  }
   G16_LAUNCH_CHECK();
 }
 
@@ -270,26 +410,34 @@ static void run_dif(const Fr* src, Fr* work, Fr* dst, size_t stride, size_t dst_
     a.logC = pl.pass[i].logC;
     a.scale_mode = last ? scale_mode : SC_NONE;
     a.bitrev_store = (last && bitrev_store) ? 1 : 0;
+    a.bitrev_load = 0;
     launch_pass(true, a, batch, stream);
   }
 }
 
-// Decimation in time over all bits: bit-reversed input order, natural-order output; in place.
-static void run_dit(Fr* data, size_t stride, int batch, int log_n, const Fr* tw, cudaStream_t stream) {
+// Decimation in time over all bits: bit-reversed input order, natural-order output; in place when src == data.
+// With gather = true the first pass reads src[bitrev(g)] instead -- natural-order input, natural-order output, the
+// permutation being 32-byte gather READS (the scattered sector writes of a bit-reversed store are what DRAM
+// handles worst) -- and the last pass can scale (SC_CONST, or SC_TABLE indexed by the natural output index).
+static void run_dit(const Fr* src, Fr* data, size_t src_stride, size_t stride, int batch, int log_n, const Fr* tw,
+                    bool gather, int scale_mode, const Fr* scale, cudaStream_t stream) {
   NttPlan pl = ntt_make_plan(log_n);
   for (int i = 0; i < pl.npass; i++) {
+    const bool first = i == 0, last = i == pl.npass - 1;
     NttPassArgs a;
-    a.src = data;
+    a.src = first ? src : data;
     a.dst = data;
-    a.src_stride = a.dst_stride = stride;
+    a.src_stride = first ? src_stride : stride;
+    a.dst_stride = stride;
     a.tw = tw;
-    a.scale = nullptr;
+    a.scale = scale;
     a.log_n = log_n;
     a.t_lo = pl.pass[i].t_lo;
     a.k = pl.pass[i].k;
     a.logC = pl.pass[i].logC;
-    a.scale_mode = SC_NONE;
+    a.scale_mode = last ? scale_mode : SC_NONE;
     a.bitrev_store = 0;
+    a.bitrev_load = (first && gather) ? 1 : 0;
     launch_pass(false, a, batch, stream);
   }
 }
@@ -323,13 +471,14 @@ static unsigned ew_grid(size_t n) {
 void ntt_prepare(int log_n, cudaStream_t stream) { (void)ntt_tables(log_n, stream); }
 
 void ntt_natural(const Fr* in, Fr* out, Fr* work, int log_n, bool inverse, cudaStream_t stream) {
-  G16_REQUIRE(in != out && work != out, "ntt_natural: output must not alias input/work");
+  G16_REQUIRE(in != out, "ntt_natural: output must not alias the input");
+  (void)work;
   NttTables& t = ntt_tables(log_n, stream);
   size_t n = (size_t)1 << log_n;
   if (inverse)
-    run_dif(in, work, out, n, n, 1, log_n, t.tw_inv.as<Fr>(), SC_CONST, t.consts.as<Fr>() + 2, true, stream);
+    run_dit(in, out, n, n, 1, log_n, t.tw_inv.as<Fr>(), true, SC_CONST, t.consts.as<Fr>() + 2, stream);
   else
-    run_dif(in, work, out, n, n, 1, log_n, t.tw_fwd.as<Fr>(), SC_NONE, nullptr, true, stream);
+    run_dit(in, out, n, n, 1, log_n, t.tw_fwd.as<Fr>(), true, SC_NONE, nullptr, stream);
 }
 
 // abc: 3n elements [Az | Bz | scratch]; on return abc is clobbered and qs holds the n scalars that
@@ -345,7 +494,7 @@ void quotient(Fr* abc, Fr* qs, int log_n, int flavour, cudaStream_t stream) {
   G16_LAUNCH_CHECK();
   // shiftEvalDomain (prover.nim:109-113) on the three vectors at once
   run_dif(abc, abc, abc, n, n, 3, log_n, t.tw_inv.as<Fr>(), SC_TABLE_BITREV, t.coset.as<Fr>(), false, stream);
-  run_dit(abc, n, 3, log_n, t.tw_fwd.as<Fr>(), stream);
+  run_dit(abc, abc, n, n, 3, log_n, t.tw_fwd.as<Fr>(), false, SC_NONE, nullptr, stream);
   if (flavour == 1) {
     k_quotient_pointwise<<<ew_grid(n), 256, 0, stream>>>(A, B, C, qs, (uint32_t)n, nullptr);
     G16_LAUNCH_CHECK();
@@ -353,8 +502,8 @@ void quotient(Fr* abc, Fr* qs, int log_n, int flavour, cudaStream_t stream) {
     ntt_ensure_coset_inv(t, stream);
     k_quotient_pointwise<<<ew_grid(n), 256, 0, stream>>>(A, B, C, A, (uint32_t)n, t.consts.as<Fr>() + 5);
     G16_LAUNCH_CHECK();
-    // inverse NTT (prover.nim:142) then * eta^-i (prover.nim:143), natural order out
-    run_dif(A, A, qs, n, n, 1, log_n, t.tw_inv.as<Fr>(), SC_TABLE_BITREV, t.coset_inv.as<Fr>(), true, stream);
+    // inverse NTT (prover.nim:142) then * eta^-i (prover.nim:143), natural order in and out
+    run_dit(A, qs, n, n, 1, log_n, t.tw_inv.as<Fr>(), true, SC_TABLE, t.coset_inv.as<Fr>(), stream);
   }
 }
 

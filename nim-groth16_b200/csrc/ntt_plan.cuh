@@ -32,6 +32,8 @@ struct NttPlan {
   NttPass pass[NTT_MAX_PASSES];   // ordered from low bits to high bits
 };
 
+// Every pass of a transform of 2^11 points or more works on full tiles (k + logC == NTT_TILE_LOG): the contiguous
+// pass owns the low 11 bits, the remaining bits are split evenly over strided passes of at most 9 bits.
 inline NttPlan ntt_make_plan(int log_n) {
   NttPlan pl;
   pl.log_n = log_n;
@@ -42,19 +44,14 @@ inline NttPlan ntt_make_plan(int log_n) {
     pl.pass[0] = NttPass{0, log_n, 0};
     return pl;
   }
-  int P = 1 + (log_n - kc + ks - 1) / ks;
-  int low = log_n - ks * (P - 1);
-  int even = (log_n + P - 1) / P;
-  if (low < even) low = even;
-  if (low > kc) low = kc;
-  pl.npass = P;
-  pl.pass[0] = NttPass{0, low, 0};
-  int rem = log_n - low, t = low;
-  for (int i = 1; i < P; i++) {
-    int k = (rem + (P - i) - 1) / (P - i);
-    int logC = NTT_TILE_LOG - k;
-    if (logC > t) logC = t;
-    pl.pass[i] = NttPass{t, k, logC};
+  const int rest = log_n - kc;
+  const int S = (rest + ks - 1) / ks;           // strided passes
+  pl.npass = 1 + S;
+  pl.pass[0] = NttPass{0, kc, 0};
+  int rem = rest, t = kc;
+  for (int i = 1; i <= S; i++) {
+    int k = (rem + (S - i + 1) - 1) / (S - i + 1);
+    pl.pass[i] = NttPass{t, k, NTT_TILE_LOG - k};
     t += k;
     rem -= k;
   }

@@ -67,6 +67,7 @@ SIGNATURES = {
     "g16_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "g16_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "g16_host_unregister": (C.c_int, [C.c_void_p]),
+    "g16_release_cached_memory": (C.c_int, []),
     "g16_msm_g1": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "g16_msm_g2": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "g16_ntt_fr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
