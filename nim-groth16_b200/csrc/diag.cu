@@ -1,6 +1,7 @@
 // Diagnostics: device self-test of the field / curve layer and the integer-pipe microbenchmark that
 // provides the IMAD roofline denominator ("this peak is not in MEASURED_PEAKS.json").
 #include <vector>
+#define G16_FP2_WHOLE_CALL   // the self-test exercises the lazily reduced Fp2 multiplication of the G2 MSM kernels
 #include "common.cuh"
 #include "ec.cuh"
 #ifdef G16_EXPERIMENTS

@@ -137,3 +137,31 @@ def test_cli_debug_intermediates_match_the_golden_fixture(exe, files, kat):
     assert got["ntt_roundtrip"] is True
     assert [int(v) for v in got["msmH"]] == [h(v) for v in g["fixed"]["msmH"]]
     assert [[int(a) for a in c] for c in got["msmB2"]] == [[h(a) for a in c] for c in g["fixed"]["msmB2"]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [2, 4])
+def test_cli_multi_gpu_reproduces_the_golden_proof(exe, files, kat, gpus):
+    """g16prove --gpus N: the compiled host calls generateProofWithMask unchanged and the library spreads the proof
+    over N devices of the process (g16_ctx_create with shard_count = -N).  Same bytes as the golden proof.  With
+    fewer than N GPUs on the box the shards share the devices that exist (G16_DEVICES), same code path."""
+    from g16b200 import export_json, _lib
+    import ctypes as C
+    z, w, tmp = files
+    n = C.c_int()
+    _lib.check(_lib.load().g16_device_count(C.byref(n)))
+    env = dict(os.environ, G16_DEVICES=",".join(str(k % n.value) for k in range(gpus)))
+    out, io = str(tmp / "proof_m.json"), str(tmp / "public_m.json")
+    one, io1 = str(tmp / "proof_1.json"), str(tmp / "public_1.json")
+    args = ["-z", z, "-w", w, "--mask-r", kat["mask"]["r"], "--mask-s", kat["mask"]["s"]]
+    r = subprocess.run([exe] + args + ["-o", one, "-i", io1], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe] + args + ["-o", out, "-i", io, "--gpus", str(gpus)], capture_output=True, text=True,
+                       timeout=600, env=env)
+    assert r.returncode == 0, r.stderr
+    assert open(out).read() == open(one).read() and open(io).read() == open(io1).read()
+    # and through the environment alone (the Nim shim's route: nothing but G16_NGPUS changes)
+    env2 = dict(env, G16_NGPUS=str(gpus))
+    r = subprocess.run([exe] + args + ["-o", out, "-i", io], capture_output=True, text=True, timeout=600, env=env2)
+    assert r.returncode == 0, r.stderr
+    assert open(out).read() == open(one).read()
