@@ -2,6 +2,8 @@
 // generateProofWithMask (groth16/prover.nim:215-304 with groth16/bn128/msm.nim:96-124) by devices of one process.
 #include "multi.cuh"
 #include <string.h>
+#include <exception>
+#include <thread>
 
 namespace g16 {
 
@@ -93,9 +95,9 @@ void MultiProver::submit(const void* witness, int form, int mem_kind, const uint
   const int G = (int)dev_.size();
   G16_REQUIRE(!in_flight(), "a proof is already in flight on this context");
   PartialsAffine* all = gathered_.as<PartialsAffine>();
-  // the device with the G2 work (the longest single kernel) is the last of the plan: enqueue it first
-  for (int i = 0; i < G; i++) {
-    const int k = G - 1 - i;
+  // one host thread per device enqueues that shard's proof (about 70 launches each): eight devices are fed in the
+  // time of one.  The calling thread takes the first device and joins the others before the finish is enqueued.
+  auto enqueue = [&](int k) {
     DeviceGuard g(dev_[k]);
     Prover& p = *shard_[k];
     p.set_mask(r, s);                     // every shard folds s*A_k + r*B1_k into its record next to its MSMs
@@ -104,7 +106,25 @@ void MultiProver::submit(const void* witness, int form, int mem_kind, const uint
     p.partials_to_affine_async(local_[k]->p);
     G16_CUDA(cudaMemcpyPeerAsync(all + k, dev_[0], local_[k]->p, dev_[k], sizeof(PartialsAffine), p.main_stream()));
     G16_CUDA(cudaEventRecord(sent_[k], p.main_stream()));
+  };
+  std::vector<std::thread> workers;
+  std::vector<std::exception_ptr> errors((size_t)G);
+  for (int k = G - 1; k >= 1; k--)        // the devices with the G2 work (the longest kernels) are the last of the plan
+    workers.emplace_back([&, k] {
+      try {
+        enqueue(k);
+      } catch (...) {
+        errors[(size_t)k] = std::current_exception();
+      }
+    });
+  try {
+    enqueue(0);
+  } catch (...) {
+    errors[0] = std::current_exception();
   }
+  for (auto& w : workers) w.join();
+  for (auto& e : errors)
+    if (e) std::rethrow_exception(e);
   DeviceGuard g(dev_[0]);
   Prover& head = *shard_[0];
   for (int k = 1; k < G; k++) G16_CUDA(cudaStreamWaitEvent(head.main_stream(), sent_[k], 0));

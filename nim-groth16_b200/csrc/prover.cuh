@@ -143,6 +143,8 @@ class Prover {
   cudaStream_t main_ = nullptr, st_mask_ = nullptr, st_[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_[24];
   cudaEvent_t gev_[4] = {nullptr, nullptr, nullptr, nullptr};   // sort of group i done (the G2 stream waits on it)
+  cudaEvent_t gdone_[4] = {nullptr, nullptr, nullptr, nullptr}; // G1 work of group i done
+  cudaStream_t st_g_[4] = {nullptr, nullptr, nullptr, nullptr}; // streams of the groups after the first
   size_t h2d_bytes_ = 0;                // witness bytes copied by the last load_witness()
   cudaEvent_t tev_[2] = {nullptr, nullptr};
   ProofOut* proof_pinned_ = nullptr;

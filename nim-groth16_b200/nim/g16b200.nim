@@ -24,6 +24,7 @@ import constantine/math/io/io_bigints
 import groth16/bn128
 import groth16/zkey_types
 import groth16/files/witness
+import std/tables
 
 {.passL: "-lg16b200".}
 
@@ -144,7 +145,13 @@ proc close*(p: G16Prover) =
     g16_ctx_destroy(p.ctx)
     p.ctx = G16Ctx(nil)
 
-proc newG16Prover*(zkey: ZKey): G16Prover =
+const
+  G16_ZKEY_TRUSTED*  = 1'u32   # skip the on-curve checks (the reference's loader already ran them, io.nim:228-236)
+  G16_ZKEY_ONE_SHOT* = 2'u32   # plain points instead of window tables: context creation is an upload
+
+proc newG16Prover*(zkey: ZKey, flags: uint32 = G16_ZKEY_TRUSTED, gpus: int = 1): G16Prover =
+  ## gpus > 1 (or the environment variable G16_NGPUS): the key is spread over that many devices of this process,
+  ## everything else -- `prove`, `close` -- is unchanged.
   g16CheckLayout()
   let packed = packCoeffs(zkey.coeffs)
   var v: G16ZkeyView
@@ -166,9 +173,33 @@ proc newG16Prover*(zkey: ZKey): G16Prover =
   copyMem(addr v.beta2,  unsafeAddr zkey.specPoints.beta2, 128)
   copyMem(addr v.delta1, unsafeAddr zkey.specPoints.delta1, 64)
   copyMem(addr v.delta2, unsafeAddr zkey.specPoints.delta2, 128)
+  v.flags = flags
   new(result)
   result.npubs = zkey.header.npubs
-  check g16_ctx_create(addr v, 0, 1, addr result.ctx)
+  check g16_ctx_create(addr v, 0, (if gpus > 1: cint(-gpus) else: cint(1)), addr result.ctx)
+
+# One resident prover per zkey: generateProofWithMask receives the ZKey with every call (prover.nim:215), the
+# device copy must not be rebuilt each time.  Keyed by the address of the H-point payload, which identifies a loaded
+# ZKey for as long as it is alive; the first proof against a key uses a ONE_SHOT context (an upload: ~80 ms at 2^20),
+# from the second proof on the key gets its window tables (~0.5 s once, ~6 ms faster per proof afterwards).
+var g16Cache {.threadvar.}: Table[pointer, tuple[prover: G16Prover, uses: int, resident: bool]]
+
+proc g16ProverFor*(zkey: ZKey): G16Prover =
+  let key = payload(zkey.pPoints.pointsH1)
+  if key notin g16Cache:
+    g16Cache[key] = (newG16Prover(zkey, G16_ZKEY_TRUSTED or G16_ZKEY_ONE_SHOT), 0, false)
+  var e = g16Cache[key]
+  inc e.uses
+  if e.uses == 2 and not e.resident:
+    e.prover.close()
+    e.prover = newG16Prover(zkey, G16_ZKEY_TRUSTED)
+    e.resident = true
+  g16Cache[key] = e
+  e.prover
+
+proc g16ReleaseProvers*() =
+  for e in g16Cache.mvalues: e.prover.close()
+  g16Cache.clear()
 
 proc prove*(p: G16Prover, witness: seq[Fr], mask_r, mask_s: Fr): (G1, G2, G1) =
   ## the masks travel as plain integers (toBig), the witness as the in-memory Montgomery seq[Fr]
@@ -187,8 +218,7 @@ proc prove*(p: G16Prover, witness: seq[Fr], mask_r, mask_s: Fr): (G1, G2, G1) =
 #   proc generateProofWithMask*( nthreads: int, printTimings: bool, zkey: ZKey, wtns: Witness, mask: Mask ): Proof =
 #     assert( zkey.header.curve == wtns.curve )                          # prover.nim:224 (kept)
 #     assert( zkey.header.nvars == wtns.values.len , "wrong witness length" )   # prover.nim:236 (kept)
-#     let prover = newG16Prover(zkey)          # or a cached instance: the zkey stays resident in HBM
-#     defer: prover.close()
+#     let prover = g16ProverFor(zkey)          # cached per ZKey: the key stays resident in HBM between proofs
 #     let (pi_a, pi_b, pi_c) = prover.prove(wtns.values, mask.r, mask.s)
 #     var pubIO = newSeq[Fr](zkey.header.npubs + 1)
 #     for i in 0..zkey.header.npubs: pubIO[i] = wtns.values[i]           # prover.nim:239-240
