@@ -82,8 +82,14 @@ class MsmAccumulator {
   static constexpr int MAX_SETS = 3;
   MsmAccumulator() {}
   ~MsmAccumulator();
-  // up to MAX_SETS point sets over the same sorted pairs, accumulated in the same launches
-  void run(const MsmSorter& sorter, const MsmPointSet<F>* sets, int nsets, cudaStream_t stream);
+  // up to MAX_SETS point sets over the same sorted pairs, accumulated in the same launches.
+  // `tail`: optional second stream (created with a HIGHER priority than `stream`) for the latency-bound end of the
+  // bucket reduction -- a handful of one-block kernels.  On the same stream (or one of equal priority) their blocks
+  // queue behind the thousands of pending blocks of whatever accumulation kernel another proof in flight has
+  // launched, and the tail of one proof no longer overlaps with the accumulation of the next.  With a tail stream
+  // the results are complete when `tail` reaches this point, `stream` is not held back.
+  void run(const MsmSorter& sorter, const MsmPointSet<F>* sets, int nsets, cudaStream_t stream,
+           cudaStream_t tail = nullptr);
   size_t workspace_bytes() const;
   bool profile = false;                // CUDA events around the accumulate kernel on `stream`
   float last_accum_ms() const;
@@ -94,6 +100,7 @@ class MsmAccumulator {
   DevBuf buckets_, partials_, winpart_;
   DevBuf tree_w_, tree_m_, tree_nodes_, tree_bp_;
   cudaEvent_t pev_[2] = {nullptr, nullptr};
+  cudaEvent_t lev_ = nullptr;          // level 1 of the reduction done (the tail stream waits for it)
 };
 
 // The reference-shaped single MSM (plain layout): sorter + accumulator.

@@ -423,6 +423,7 @@ template <class F>
 MsmAccumulator<F>::~MsmAccumulator() {
   for (int i = 0; i < 2; i++)
     if (pev_[i]) cudaEventDestroy(pev_[i]);
+  if (lev_) cudaEventDestroy(lev_);
 }
 template <class F>
 size_t MsmAccumulator<F>::workspace_bytes() const {
@@ -513,14 +514,22 @@ void MsmAccumulator<F>::run_tree(const MsmSorter& sorter, const MsmPointSet<F>* 
 #endif
 
 template <class F>
-void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, int nsets, cudaStream_t stream) {
+void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, int nsets, cudaStream_t stream,
+                            cudaStream_t tail) {
   G16_REQUIRE(nsets >= 1 && nsets <= MAX_SETS, "MsmAccumulator: 1..3 point sets");
   const MsmGeometry& g = sorter.geom();
   G16_REQUIRE(g.nwin <= MSM_MAX_WINDOWS, "too many windows");
   // bucket reduction plan (msm_reduce_plan.cuh): running sums over 16 consecutive buckets (level 1), over 8
   // consecutive entries of the result when it is still long (level 2), then the bit-sliced sum of what is left
   const uint32_t nsetsB = g.precomp ? 1u : (uint32_t)g.nwin;
-  const ReducePlan rp = msm_reduce_plan(g.nb);
+  static int l1_max = -1, l2_min = -1;
+  if (l1_max < 0) {
+    const char* e = getenv("G16_REDUCE_L1");          // experiment knobs: length of the level-1 running sums ...
+    l1_max = e ? atoi(e) : 16;
+    const char* e2 = getenv("G16_REDUCE_L2MIN");      // ... and the array length from which level 2 runs
+    l2_min = e2 ? atoi(e2) : 8192;
+  }
+  const ReducePlan rp = msm_reduce_plan(g.nb, (uint32_t)l1_max, (uint32_t)l2_min);
   G16_REQUIRE(rp.ok, "too many buckets for the reduction");
   const uint32_t L1 = rp.L1, n1 = rp.n1, L2 = rp.L2, n2 = rp.n2, tpb1 = rp.tpb1, blocks1 = rp.blocks1, tpb2 = rp.tpb2,
                  blocks2 = rp.blocks2, nbits = rp.nbits, nchunks = rp.nchunks, first_bit_level = rp.first_bit_level,
@@ -615,6 +624,12 @@ void MsmAccumulator<F>::run(const MsmSorter& sorter, const MsmPointSet<F>* in, i
   }
   k_reduce_level<F><<<dim3(blocks1, nsetsB, (unsigned)nsets), tpb1, tpb1 * sizeof(XYZZ<F>), stream>>>(lv1);
   G16_LAUNCH_CHECK();
+  if (tail && tail != stream) {           // everything below is latency-bound: continue on the high-priority stream
+    if (!lev_) G16_CUDA(cudaEventCreateWithFlags(&lev_, cudaEventDisableTiming));
+    G16_CUDA(cudaEventRecord(lev_, stream));
+    G16_CUDA(cudaStreamWaitEvent(tail, lev_, 0));
+    stream = tail;
+  }
   if (L2 > 1) {
     k_reduce_level<F><<<dim3(blocks2, nsetsB, (unsigned)nsets), tpb2, tpb2 * sizeof(XYZZ<F>), stream>>>(lv2);
     G16_LAUNCH_CHECK();

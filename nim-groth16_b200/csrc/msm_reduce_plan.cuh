@@ -25,15 +25,15 @@ struct ReducePlan {
   bool ok;
 };
 
-inline ReducePlan msm_reduce_plan(uint32_t nb) {
+inline ReducePlan msm_reduce_plan(uint32_t nb, uint32_t l1_max = 16, uint32_t l2_min_n1 = 8192) {
   auto ilog2 = [](uint32_t v) { uint32_t l = 0; while ((1u << l) < v) l++; return l; };
   auto tpb_for = [](uint32_t threads) { return threads < 128u ? (threads < 32u ? 32u : threads) : 128u; };
   ReducePlan p;
   // (shorter running sums with more bit slicing were tried for small bucket sets: less latency per MSM but more
   // work, and a sharded proof is throughput-bound in aggregate: 1/8 shard 5.27 -> 5.60 ms; not kept)
-  p.L1 = nb >= 16u ? 16u : nb;
+  p.L1 = nb >= l1_max ? l1_max : nb;
   p.n1 = nb / p.L1;
-  p.L2 = p.n1 >= 8192u ? 8u : 1u;                 // level 2 only pays for itself on long arrays
+  p.L2 = p.n1 >= l2_min_n1 ? 8u : 1u;             // level 2 only pays for itself on long arrays
   p.n2 = p.n1 / p.L2;
   p.tpb1 = tpb_for(p.n1);
   p.blocks1 = (p.n1 + p.tpb1 - 1) / p.tpb1;

@@ -596,7 +596,13 @@ Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_
       g = groups.back().get();
       g->lo = pc.lo;
       g->hi = pc.hi;
-      g->geom = msm_geometry(pc.hi - pc.lo, msm_pick_window(pc.hi - pc.lo, precomp), precomp);
+      int c = msm_pick_window(pc.hi - pc.lo, precomp);
+      if (const char* e = getenv("G16_C_DELTA")) {           // experiment knob: window of the sharded pieces
+        if (shard_count > 1) c += atoi(e);
+        if (c < 4) c = 4;
+        if (c > 22) c = 22;
+      }
+      g->geom = msm_geometry(pc.hi - pc.lo, c, precomp);
     }
     if (pc.which == 3) g->has_b2 = true;
     else g->which1[g->nsets1++] = pc.which;
@@ -725,7 +731,10 @@ void Prover::init_slot() {
   G16_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));      // hi is numerically smaller
   int p_mid = prio_hi + (prio_lo - prio_hi) / 2;
   G16_CUDA(cudaStreamCreateWithPriority(&main_, cudaStreamNonBlocking, prio_hi));
-  int pr[3] = {prio_lo, p_mid, prio_hi};              // ABC+quotient+H1 | witness sort, A1+B1+C1 | B2
+  // the latency-bound tails (bucket-reduction ends, assembly) sit above every throughput-bound kernel: a one-block
+  // kernel must not queue behind the pending blocks of another proof's accumulation (see MsmAccumulator::run)
+  const int p_b2 = prio_hi < prio_lo ? prio_hi + 1 : prio_hi;
+  int pr[3] = {prio_lo, p_mid > p_b2 ? p_mid : p_b2, p_b2};   // ABC+quotient+H1 | witness sort, A1+B1+C1 | B2
   if (const char* e = getenv("G16_STREAM_PRIO"))      // experiment knob: three letters of l/m/h
     for (int i = 0; i < 3 && e[i]; i++) pr[i] = e[i] == 'h' ? prio_hi : e[i] == 'm' ? p_mid : prio_lo;
   G16_CUDA(cudaStreamCreateWithPriority(&st_[0], cudaStreamNonBlocking, pr[0]));
@@ -736,6 +745,10 @@ void Prover::init_slot() {
   for (auto& g : R->groups) {
     (void)g;
     gw_.emplace_back(new GroupWork());
+  }
+  for (int i = 0; i < 6; i++) {
+    G16_CUDA(cudaStreamCreateWithPriority(&tail_[i], cudaStreamNonBlocking, prio_hi));
+    G16_CUDA(cudaEventCreateWithFlags(&tdone_[i], cudaEventDisableTiming));
   }
   for (int i = 0; i < 4; i++) {
     G16_CUDA(cudaEventCreateWithFlags(&gev_[i], cudaEventDisableTiming));
@@ -775,6 +788,10 @@ Prover::~Prover() {
   cudaDeviceSynchronize();
   for (int i = 0; i < 24; i++)
     if (ev_[i]) cudaEventDestroy(ev_[i]);
+  for (int i = 0; i < 6; i++) {
+    if (tail_[i]) cudaStreamDestroy(tail_[i]);
+    if (tdone_[i]) cudaEventDestroy(tdone_[i]);
+  }
   for (int i = 0; i < 4; i++) {
     if (gev_[i]) cudaEventDestroy(gev_[i]);
     if (gdone_[i]) cudaEventDestroy(gdone_[i]);
@@ -859,9 +876,12 @@ void Prover::run_msms(g16_stats* stats) {
     MsmPointSet<Fp> hs;
     hs.points = R->tabH1.as<G1Affine>();
     hs.result = &res->h1;
-    accH_.run(sortH_, &hs, 1, st_[0]);
+    accH_.run(sortH_, &hs, 1, st_[0], tail_[0]);
+  } else {
+    G16_CUDA(cudaEventRecord(ev_[12], st_[0]));
+    G16_CUDA(cudaStreamWaitEvent(tail_[0], ev_[12], 0));
   }
-  G16_CUDA(cudaEventRecord(ev_[4], st_[0]));
+  G16_CUDA(cudaEventRecord(ev_[4], tail_[0]));
 
   // stream 1: per group one digit/sort pass over its witness range, then its G1 sets in the same launches
   // (prover.nim:282, 288, 302; zs = witness[npubs+1 ..] through the padded C1 table); stream 2: the G2 set
@@ -883,8 +903,8 @@ void Prover::run_msms(g16_stats* stats) {
       MsmPointSet<Fp2> bs;
       bs.points = g.tabB2.as<G2Affine>();
       bs.result = &res->b2;
-      gw.acc2.run(gw.sort, &bs, 1, st_[2]);
-      G16_CUDA(cudaEventRecord(ev_[9], st_[2]));
+      gw.acc2.run(gw.sort, &bs, 1, st_[2], tail_[1]);
+      G16_CUDA(cudaEventRecord(ev_[9], tail_[1]));
     }
     if (g.nsets1) {
       MsmPointSet<Fp> ws[3];
@@ -892,39 +912,44 @@ void Prover::run_msms(g16_stats* stats) {
         ws[k].points = g.tab1[k].as<G1Affine>();
         ws[k].result = g.which1[k] == 0 ? &res->a1 : g.which1[k] == 1 ? &res->b1 : &res->c1;
       }
-      gw.acc1.run(gw.sort, ws, g.nsets1, sg);
-    }
-    if (gi > 0) {                                          // join the group's stream into stream 1
-      G16_CUDA(cudaEventRecord(gdone_[gi], sg));
-      G16_CUDA(cudaStreamWaitEvent(st_[1], gdone_[gi], 0));
+      gw.acc1.run(gw.sort, ws, g.nsets1, sg, tail_[2 + gi]);
+      if (gi > 0) {                                        // join the group's tail into the tail of group 0
+        G16_CUDA(cudaEventRecord(gdone_[gi], tail_[2 + gi]));
+        G16_CUDA(cudaStreamWaitEvent(tail_[2], gdone_[gi], 0));
+      }
     }
   }
+  // tail_[2] now follows every G1 group of this shard; it also has to follow stream 1 itself when no group has
+  // G1 sets (nothing was handed over to it)
+  G16_CUDA(cudaEventRecord(ev_[16], st_[1]));
+  G16_CUDA(cudaStreamWaitEvent(tail_[2], ev_[16], 0));
   if (R->groups.empty()) G16_CUDA(cudaEventRecord(ev_[6], st_[1]));
   bool any_b2 = false;
   for (auto& g : R->groups) any_b2 = any_b2 || g->has_b2;
   if (!any_b2) {
     G16_CUDA(cudaEventRecord(ev_[8], st_[2]));
-    G16_CUDA(cudaEventRecord(ev_[9], st_[2]));
+    G16_CUDA(cudaStreamWaitEvent(tail_[1], ev_[8], 0));
+    G16_CUDA(cudaEventRecord(ev_[9], tail_[1]));
   }
-  G16_CUDA(cudaEventRecord(ev_[7], st_[1]));
+  G16_CUDA(cudaEventRecord(ev_[7], tail_[2]));
   if (masked_partials_) {
     // this shard's share of s ** pi_a + r ** rho, folded into its c1 partial while B2 / H are still in flight
     if (R->owns_ab) {
-      G16_CUDA(cudaStreamWaitEvent(st_[1], ev_[23], 0));
-      k_shard_early<<<1, 256, 0, st_[1]>>>(results_.as<MsmResults>(), mask_.as<MaskTerms>(), early_.as<G1XYZZ>() + 1);
+      G16_CUDA(cudaStreamWaitEvent(tail_[2], ev_[23], 0));
+      k_shard_early<<<1, 256, 0, tail_[2]>>>(results_.as<MsmResults>(), mask_.as<MaskTerms>(), early_.as<G1XYZZ>() + 1);
       G16_LAUNCH_CHECK();
     }
   } else if (mask_started_ && R->shard_count == 1) {
     // the MSM-dependent scalar multiplications start now and overlap with the B2 / H work still in flight
-    G16_CUDA(cudaStreamWaitEvent(st_[1], ev_[23], 0));
-    k_assemble_early<<<1, 256, 0, st_[1]>>>(results_.as<MsmResults>(), mask_.as<MaskTerms>(), proof_.as<g16_proof>(),
+    G16_CUDA(cudaStreamWaitEvent(tail_[2], ev_[23], 0));
+    k_assemble_early<<<1, 256, 0, tail_[2]>>>(results_.as<MsmResults>(), mask_.as<MaskTerms>(), proof_.as<g16_proof>(),
                                             early_.as<G1XYZZ>(), early_.as<G1XYZZ>() + 1);
     G16_LAUNCH_CHECK();
     early_done_ = true;
   }
 
-  for (int i = 0; i < 3; i++) {
-    G16_CUDA(cudaEventRecord(ev_[13 + i], st_[i]));
+  for (int i = 0; i < 3; i++) {                        // H chain, B2, G1 groups (+ early assembly): join the tails
+    G16_CUDA(cudaEventRecord(ev_[13 + i], tail_[i]));
     G16_CUDA(cudaStreamWaitEvent(main_, ev_[13 + i], 0));
   }
   G16_CUDA(cudaEventRecord(ev_[18], main_));

@@ -145,6 +145,9 @@ class Prover {
   cudaEvent_t gev_[4] = {nullptr, nullptr, nullptr, nullptr};   // sort of group i done (the G2 stream waits on it)
   cudaEvent_t gdone_[4] = {nullptr, nullptr, nullptr, nullptr}; // G1 work of group i done
   cudaStream_t st_g_[4] = {nullptr, nullptr, nullptr, nullptr}; // streams of the groups after the first
+  // high-priority streams for the latency-bound tails: [0] H chain, [1] B2, [2..5] the G1 work of group 0..3
+  cudaStream_t tail_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t tdone_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t h2d_bytes_ = 0;                // witness bytes copied by the last load_witness()
   cudaEvent_t tev_[2] = {nullptr, nullptr};
   ProofOut* proof_pinned_ = nullptr;

@@ -180,8 +180,10 @@ proc newG16Prover*(zkey: ZKey, flags: uint32 = G16_ZKEY_TRUSTED, gpus: int = 1):
 
 # One resident prover per zkey: generateProofWithMask receives the ZKey with every call (prover.nim:215), the
 # device copy must not be rebuilt each time.  Keyed by the address of the H-point payload, which identifies a loaded
-# ZKey for as long as it is alive; the first proof against a key uses a ONE_SHOT context (an upload: ~80 ms at 2^20),
-# from the second proof on the key gets its window tables (~0.5 s once, ~6 ms faster per proof afterwards).
+# ZKey for as long as it is alive.  A key starts on a ONE_SHOT context (an upload: ~80 ms at 2^20 including its first
+# proof); the window tables cost ~0.5 s once and save ~6 ms per proof, i.e. they pay off after ~90 proofs, so the key
+# is promoted to a resident context at its 64th proof (the classic rent-or-buy rule: never worse than twice the best
+# choice made with hindsight).  A host that knows it will prove many times calls newG16Prover(zkey) itself.
 var g16Cache {.threadvar.}: Table[pointer, tuple[prover: G16Prover, uses: int, resident: bool]]
 
 proc g16ProverFor*(zkey: ZKey): G16Prover =
@@ -190,7 +192,7 @@ proc g16ProverFor*(zkey: ZKey): G16Prover =
     g16Cache[key] = (newG16Prover(zkey, G16_ZKEY_TRUSTED or G16_ZKEY_ONE_SHOT), 0, false)
   var e = g16Cache[key]
   inc e.uses
-  if e.uses == 2 and not e.resident:
+  if e.uses == 64 and not e.resident:
     e.prover.close()
     e.prover = newG16Prover(zkey, G16_ZKEY_TRUSTED)
     e.resident = true
