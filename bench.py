@@ -264,6 +264,7 @@ def run_ours(args):
     nvars = zk.nvars
     w_np = np.ascontiguousarray(wit, dtype=np.uint64)
     w_pinned = torch.from_numpy(w_np.view(np.int64).copy()).pin_memory()
+    w_pinned_rows = w_pinned.view(-1, 4)
     w_dev = w_pinned.to("cuda")
     d2h_bytes = 256
 
@@ -298,7 +299,8 @@ def run_ours(args):
 
         def make_runner(ptr, mem_kind, d=None):
             # per proof and rank: partial sums -> NCCL all-gather -> assembly, all enqueued without a host
-            # synchronisation (ShardedProver.exchange_submit); the host only waits for the finished proof
+            # synchronisation (ShardedProver.exchange_submit); the host only waits for the finished proof.
+            # Host witness: every rank uploads 1/N of it and the slices are all-gathered over NVLink.
             def run(steps):
                 dd = d or depth
                 last = None
@@ -306,7 +308,10 @@ def run_ours(args):
                     sp = sps[i % dd]
                     if i >= dd:
                         last = sp.wait()
-                    sp.partials_submit(ptr, mem_kind, mask)
+                    if mem_kind == MEM_HOST and not args.no_scatter:
+                        sp.partials_submit_host(w_pinned_rows, mask)
+                    else:
+                        sp.partials_submit(ptr, mem_kind, mask)
                     sp.exchange_submit(mask)
                 for i in range(min(dd, steps)):
                     last = sps[(steps - min(dd, steps) + i) % dd].wait()
@@ -343,6 +348,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     e2e_dev_ms, e2e_wall_ms, _, raw2 = timed(run_e2e, args.steps, max(depth, args.warmup // 2))
     h2d_bytes = ctx.last_witness_bytes()               # what this rank actually copied for its last proof
+    if world > 1 and not args.no_scatter:
+        h2d_bytes = sps[0].h2d_bytes                   # its slice of the witness; the rest arrives over NVLink
     seq = None
     seq_dev_ms, seq_wall_ms, _, raw3 = timed(make_runner(w_dev.data_ptr(), MEM_DEVICE, 1), args.steps, 2)
     stats = dict(ctx.last_stats or {})                 # phases of a strictly sequential proof on this rank
@@ -389,8 +396,8 @@ def run_ours(args):
                "e2e": {"value": args.steps / (e2e_wall_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": total_h2d,
                        "d2h_bytes_per_step": d2h_bytes, "device_ms_per_step": e2e_dev_ms / args.steps,
                        "wall_ms_per_step": e2e_wall_ms / args.steps,
-                       "note": "pinned host witness; every rank copies only the witness intervals its shard reads "
-                               "(h2d_bytes_per_step = sum over ranks)",
+                       "note": "pinned host witness; one process per GPU: every rank uploads 1/N of it over its own PCIe "
+                               "link and the slices are all-gathered over NVLink (h2d_bytes_per_step = sum over ranks)",
                        "api": "g16_prove_submit/wait (host witness)" if world == 1 else
                               "g16_ctx_set_mask + g16_prove_partials_submit + g16_ctx_order_stream + NCCL all-gather + "
                               "g16_prove_finish_submit + g16_prove_wait"},
@@ -725,6 +732,7 @@ def main():
                     help="cpu_baseline of the main arm: constraints (log2) of the one CPU proof that is timed")
     ap.add_argument("--pipeline", type=int, default=2, help="proofs in flight (1 = strictly sequential proofs)")
     ap.add_argument("--validate", action="store_true", help="validate the points in the timed contexts too")
+    ap.add_argument("--no-scatter", action="store_true", help="N > 1: every rank copies the witness intervals it reads itself")
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--make-fixture", default=None, help=argparse.SUPPRESS)

@@ -77,6 +77,20 @@ MsmGeometry msm_geometry(size_t n, int c, bool precomp, int tree_log) {
   size_t T = g.m / 150000;
   if (T < 2 * avg + 16) T = 2 * avg + 16;
   if (T > 32768) T = 32768;
+  // Few buckets (a small window: the pieces of a sharded proof, mid-size MSMs): one item per bucket would launch fewer
+  // threads than the GPU holds for a few waves (4 CTAs x 128 threads x 148 SMs = 76k), and the kernel then runs at
+  // ~64 % of its rate (measured: 2^18-point shards at c = 17).  Regular buckets are then split as well, into items of
+  // m / 300k additions (at least 16, so the extra full additions of the fixup stay below ~9 % of the bucket's work).
+  static int target_items = -1;
+  if (target_items < 0) {
+    const char* e = getenv("G16_MSM_TARGET_ITEMS");
+    target_items = e ? atoi(e) : 300000;
+  }
+  if (target_items > 0 && g.nbuckets < (uint32_t)target_items) {
+    size_t t2 = g.m / (size_t)target_items;
+    if (t2 < 16) t2 = 16;
+    if (t2 < T) T = t2;
+  }
   g.tree_log = tree_log < 0 ? default_tree_log() : tree_log;
   if (g.tree_log) T = (size_t)1 << g.tree_log;   // chunks of the batched-affine tree (msm_tree.cuh)
   g.T = (uint32_t)T;

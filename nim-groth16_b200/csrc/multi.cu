@@ -1,6 +1,7 @@
 // In-library multi-GPU prover (see multi.cuh).  Replaces the thread-pool parallelism inside
 // generateProofWithMask (groth16/prover.nim:215-304 with groth16/bn128/msm.nim:96-124) by devices of one process.
 #include "multi.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include <exception>
 #include <thread>
@@ -62,6 +63,7 @@ MultiProver::MultiProver(const MultiProver& base) : dev_(base.dev_) {
 
 void MultiProver::init_slot() {
   const int G = (int)dev_.size();
+  if (const char* e = getenv("G16_WITNESS_SCATTER")) scatter_witness_ = e[0] != '0';
   for (int k = 0; k < G; k++) {
     DeviceGuard g(dev_[k]);
     local_.emplace_back(new DevBuf());
@@ -97,11 +99,48 @@ void MultiProver::submit(const void* witness, int form, int mem_kind, const uint
   PartialsAffine* all = gathered_.as<PartialsAffine>();
   // one host thread per device enqueues that shard's proof (about 70 launches each): eight devices are fed in the
   // time of one.  The calling thread takes the first device and joins the others before the finish is enqueued.
+  // A host witness travels ONCE over PCIe: device k uploads the k-th of G slices over its own link, then every device
+  // pulls the parts of the intervals it reads from the devices that hold them (NVLink peer copies ordered by events)
+  // -- instead of up to G copies of the whole witness competing for the host's PCIe lanes.
+  const bool scatter = mem_kind == G16_MEM_HOST && G > 1 && scatter_witness_;
+  const size_t nv = shard_[0]->nvars();
+  auto slice = [&](int k, size_t& lo, size_t& hi) {
+    lo = nv * (size_t)k / (size_t)G;
+    hi = k == G - 1 ? nv : nv * (size_t)(k + 1) / (size_t)G;
+  };
+  if (scatter) {
+    G16_REQUIRE(witness != nullptr, "witness is null");
+    for (int k = 0; k < G; k++) {
+      DeviceGuard g(dev_[k]);
+      size_t lo, hi;
+      slice(k, lo, hi);
+      shard_[k]->witness_begin(form);
+      shard_[k]->witness_upload(witness, form, lo, hi);
+    }
+  }
   auto enqueue = [&](int k) {
     DeviceGuard g(dev_[k]);
     Prover& p = *shard_[k];
     p.set_mask(r, s);                     // every shard folds s*A_k + r*B1_k into its record next to its MSMs
-    p.load_witness(witness, form, mem_kind);
+    if (scatter) {
+      for (const auto& iv : p.witness_needs())
+        for (int j = 0; j < G; j++) {
+          if (j == k) continue;
+          size_t lo, hi;
+          slice(j, lo, hi);
+          if (lo < iv.first) lo = iv.first;
+          if (hi > iv.second) hi = iv.second;
+          if (hi <= lo) continue;
+          G16_CUDA(cudaStreamWaitEvent(p.main_stream(), shard_[j]->witness_uploaded(), 0));
+          G16_CUDA(cudaMemcpyPeerAsync(p.witness_raw(form) + lo, dev_[k], shard_[j]->witness_raw(form) + lo, dev_[j],
+                                       (hi - lo) * sizeof(Fr), p.main_stream()));
+        }
+      size_t lo, hi;
+      slice(k, lo, hi);
+      p.witness_finish(form, (hi - lo) * sizeof(Fr));
+    } else {
+      p.load_witness(witness, form, mem_kind);
+    }
     p.run_msms(nullptr);
     p.partials_to_affine_async(local_[k]->p);
     G16_CUDA(cudaMemcpyPeerAsync(all + k, dev_[0], local_[k]->p, dev_[k], sizeof(PartialsAffine), p.main_stream()));

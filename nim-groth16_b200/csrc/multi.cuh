@@ -44,6 +44,7 @@ class MultiProver {
   std::vector<std::unique_ptr<DevBuf>> local_;          // device k: its own partial record
   std::vector<cudaEvent_t> sent_;                       // record k has arrived in gathered_
   DevBuf gathered_;                                     // first device: count() records
+  bool scatter_witness_ = true;                         // host witness: one PCIe upload in G slices + NVLink exchange
 };
 
 }  // namespace g16

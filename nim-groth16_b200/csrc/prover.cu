@@ -849,6 +849,31 @@ void Prover::load_witness(const void* w, int form, int mem_kind) {
   G16_CUDA(cudaEventRecord(ev_[21], main_));
 }
 
+void Prover::witness_begin(int form) {
+  G16_REQUIRE(form == G16_FORM_MONT || form == G16_FORM_STD, "unknown witness form");
+  G16_CUDA(cudaEventRecord(ev_[20], main_));
+  if (form == G16_FORM_MONT) staging_.ensure((size_t)R->nvars * sizeof(Fr));
+}
+void Prover::witness_upload(const void* w_host, int form, size_t lo, size_t hi) {
+  if (hi > lo)
+    G16_CUDA(cudaMemcpyAsync(witness_raw(form) + lo, reinterpret_cast<const Fr*>(w_host) + lo, (hi - lo) * sizeof(Fr),
+                             cudaMemcpyHostToDevice, main_));
+  // standard-form values are canonicalised before the slice is exposed to the peers (later reductions of the same
+  // elements then never write, so a peer copy cannot observe a half-written element)
+  if (hi > lo && form == G16_FORM_STD) fr_reduce_std(witness_.as<Fr>() + lo, hi - lo, main_);
+  G16_CUDA(cudaEventRecord(ev_[17], main_));
+}
+void Prover::witness_finish(int form, size_t h2d_bytes) {
+  for (const auto& iv : R->witness_needs) {
+    const size_t cnt = iv.second - iv.first;
+    if (!cnt) continue;
+    if (form == G16_FORM_STD) fr_reduce_std(witness_.as<Fr>() + iv.first, cnt, main_);
+    else fr_from_mont(staging_.as<Fr>() + iv.first, witness_.as<Fr>() + iv.first, cnt, main_);
+  }
+  h2d_bytes_ = h2d_bytes;
+  G16_CUDA(cudaEventRecord(ev_[21], main_));
+}
+
 void Prover::run_msms(g16_stats* stats) {
   // an announced mask serves ONE set of partial sums: without a new g16_ctx_set_mask the records are plain again
   if (masked_partials_ && mask_used_) {

@@ -94,6 +94,19 @@ class Prover {
   std::shared_ptr<Resident> resident() const { return R; }
   // witness upload (host or device source) into the resident standard-form buffer
   void load_witness(const void* w, int form, int mem_kind);
+  // The same in three steps, for a host witness that several devices of one process share (multi.cu): every device
+  // uploads ONE slice over its own PCIe link, the devices then exchange slices over NVLink.
+  //   witness_begin     start of the phase (timing event), staging buffer for Montgomery input
+  //   witness_raw       the buffer raw values land in (staging for Montgomery input, the witness buffer otherwise)
+  //   witness_upload    H2D of elements [lo, hi) into witness_raw on the main stream; witness_uploaded() fires after it
+  //   witness_finish    after the missing parts of the needed intervals have been copied in on the main stream:
+  //                     conversion / reduction of the needed intervals
+  void witness_begin(int form);
+  Fr* witness_raw(int form) { return form == G16_FORM_MONT ? staging_.as<Fr>() : witness_.as<Fr>(); }
+  void witness_upload(const void* w_host, int form, size_t lo, size_t hi);
+  cudaEvent_t witness_uploaded() const { return ev_[17]; }
+  void witness_finish(int form, size_t h2d_bytes);
+  const std::vector<std::pair<size_t, size_t>>& witness_needs() const { return R->witness_needs; }
   void run_msms(g16_stats* stats);                     // ABC, quotient, five MSMs -> results_ (asynchronous)
   void collect_stats(g16_stats* stats);                // phase times of the last run (after completion)
   void partials_to_affine(void* partials_dev);         // results_ -> g16_partials (device), synchronous

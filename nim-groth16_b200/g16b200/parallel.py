@@ -73,6 +73,30 @@ class ShardedProver:
         _lib.check(_lib.load().g16_prove_partials_submit(self.ctx._h, witness_ptr, FORM_STD, mem_kind,
                                                          self.partials.data_ptr()))
 
+    def partials_submit_host(self, witness_pinned: "torch.Tensor", mask: Optional[Mask] = None, group=None):   # noqa: F821
+        """Host witness (a pinned torch tensor of nvars x 4 int64 limbs, standard form), travelling ONCE over PCIe: this
+        rank uploads the rank-th of `world` slices over its own link, the slices are all-gathered over NVLink (NCCL), and
+        the partial sums read the gathered device copy -- instead of every rank pulling the intervals it needs (up to
+        the whole witness) through the host's PCIe lanes at the same time.  Ordered on the device like
+        exchange_submit(): no host synchronisation."""
+        import torch
+        import torch.distributed as dist
+        lib = _lib.load()
+        n = witness_pinned.shape[0]
+        per = -(-n // self.world)
+        if getattr(self, "_wbuf", None) is None or self._wbuf.shape[0] != per * self.world:
+            self._wbuf = torch.zeros((per * self.world, 4), dtype=torch.int64, device=self.device)
+        lo, hi = min(n, per * self.rank), min(n, per * (self.rank + 1))
+        mine = self._wbuf[per * self.rank: per * (self.rank + 1)]
+        if hi > lo:
+            mine[: hi - lo].copy_(witness_pinned[lo:hi], non_blocking=True)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._wbuf.view(-1), mine.reshape(-1), group=group)
+        st = torch.cuda.current_stream(self.device)
+        _lib.check(lib.g16_ctx_order_stream(self.ctx._h, st.cuda_stream, 1))     # the context waits for the gather
+        self.h2d_bytes = (hi - lo) * 32
+        self.partials_submit(self._wbuf.data_ptr(), MEM_DEVICE, mask)
+
     def exchange_submit(self, mask: Mask, group=None):
         """Enqueues the all-gather of the partial records and the assembly behind this rank's partial sums, ordered
         on the device (g16_ctx_order_stream): the NCCL stream waits for the record, the context waits for the
