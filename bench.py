@@ -516,6 +516,35 @@ def inlib_line(args, g, lib, zk, w_pinned, w_dev, mask, raw_ref, world, torch):
         slots[0].wait()
     res["sequential_ms_per_proof"] = (time.perf_counter() - t0) / args.steps * 1e3
     res["witness_bytes_per_proof"] = ctx.last_witness_bytes()
+    res["e2e"]["witness"] = "pinned host memory, uploaded once in %d slices (one per device) + NVLink peer copies" % world
+    # the other way to bring a host witness in: every device uploads the intervals its shard reads itself
+    os.environ["G16_WITNESS_SCATTER"] = "0"
+    try:
+        alt = g.ProverContext(zk, devices=world, trusted=True)
+        aslots = [alt, alt.clone()]
+
+        def run2(steps):
+            last = None
+            for i in range(steps):
+                c = aslots[i % 2]
+                if i >= 2:
+                    last = c.wait()[0]
+                c.submit(w_pinned.data_ptr(), mask, E.FORM_STD, MEM_HOST)
+            for i in range(min(2, steps)):
+                last = aslots[(steps - min(2, steps) + i) % 2].wait()[0]
+            return last
+        run2(3)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        raw = run2(args.steps)
+        dt = time.perf_counter() - t0
+        assert bytes(raw.pi_c) == bytes(raw_ref.pi_c)
+        res["e2e_direct_upload"] = {"proofs_per_s": args.steps / dt, "ms_per_proof": dt / args.steps * 1e3,
+                                    "witness_bytes_per_proof": alt.last_witness_bytes()}
+        for c in aslots:
+            c.close()
+    finally:
+        del os.environ["G16_WITNESS_SCATTER"]
     res["context_create_s"] = create_s
     res["api"] = "g16_ctx_create(zkey, 0, -%d) + g16_prove_submit/wait: one process, %d devices, peer copies" % (world, world)
     res["same_proof_as_nccl_path"] = True

@@ -24,6 +24,8 @@ const char* get_last_error() { return t_last_error.c_str(); }
 
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launches(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+uint64_t launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 
 // per-device internal stream of the stream-ordered allocator (DevBuf); the pool keeps freed memory cached
 static std::mutex g_pool_mu;

@@ -31,6 +31,8 @@ struct Error : public std::runtime_error {
 
 // every kernel launch of the library is followed by exactly one G16_LAUNCH_CHECK()
 void count_launch();   // capi.cu
+void count_launches(uint64_t n);   // capi.cu: kernels replayed by a CUDA graph launch
+uint64_t launches_so_far();        // capi.cu
 #define G16_LAUNCH_CHECK()       \
   do {                           \
     g16::count_launch();         \

@@ -724,6 +724,7 @@ size_t Resident::bytes() const {
 
 void Prover::init_slot() {
   for (int i = 0; i < 24; i++) ev_[i] = nullptr;
+  if (const char* e = getenv("G16_GRAPH")) use_graph_ = atoi(e);
   // Priorities order the kernels that compete for the SMs: the witness sort and the G2 MSM (longest
   // latency-bound reduction tail) first, then the fused G1 witness MSMs (their result feeds the early
   // assembly), the H chain last -- so the single-warp tails of one MSM overlap with the accumulation of another.
@@ -786,6 +787,8 @@ size_t Prover::resident_bytes() const {
 
 Prover::~Prover() {
   cudaDeviceSynchronize();
+  for (auto& g : graphs_)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   for (int i = 0; i < 24; i++)
     if (ev_[i]) cudaEventDestroy(ev_[i]);
   for (int i = 0; i < 6; i++) {
@@ -874,13 +877,62 @@ void Prover::witness_finish(int form, size_t h2d_bytes) {
   G16_CUDA(cudaEventRecord(ev_[21], main_));
 }
 
+// The per-proof DAG (about 70 launches on up to a dozen streams) is the same every time for a given context slot and
+// mode.  With G16_GRAPH=1 it is captured once -- on the slot's second proof, when every workspace exists -- and
+// replayed as ONE graph launch: no per-launch host cost, no launch gaps between the small dependent kernels.
+// Per-phase timing events are not available in that mode (g16_stats phases read 0).
 void Prover::run_msms(g16_stats* stats) {
+  (void)stats;   // phase times are read by collect_stats() once the work has completed
   // an announced mask serves ONE set of partial sums: without a new g16_ctx_set_mask the records are plain again
   if (masked_partials_ && mask_used_) {
     masked_partials_ = false;
     mask_started_ = false;
   }
   mask_used_ = true;
+  const int mode = masked_partials_ ? 1 : (mask_started_ && R->shard_count == 1) ? 2 : 0;
+  GraphSlot& gs = graphs_[mode];
+  if (use_graph_ && runs_ >= 1 && !gs.failed) {
+    // the mask terms come from a stream outside the graph: order them before it
+    if (mode != 0) G16_CUDA(cudaStreamWaitEvent(main_, ev_[23], 0));
+    if (!gs.exec) {
+      cudaGraph_t graph = nullptr;
+      const uint64_t l0 = launches_so_far();
+      cudaError_t e = cudaStreamBeginCapture(main_, cudaStreamCaptureModeRelaxed);
+      if (e == cudaSuccess) {
+        try {
+          run_msms_body(true);
+        } catch (...) {
+          cudaStreamEndCapture(main_, &graph);
+          if (graph) cudaGraphDestroy(graph);
+          cudaGetLastError();
+          gs.failed = true;
+          throw;
+        }
+        e = cudaStreamEndCapture(main_, &graph);
+      }
+      if (e == cudaSuccess) e = cudaGraphInstantiate(&gs.exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (e != cudaSuccess) {               // capture not possible here: fall back to plain launches for good
+        cudaGetLastError();
+        gs.exec = nullptr;
+        gs.failed = true;
+      } else {
+        gs.launches = launches_so_far() - l0;
+      }
+    }
+    if (gs.exec) {
+      G16_CUDA(cudaGraphLaunch(gs.exec, main_));
+      count_launches(gs.launches);
+      if (mode == 2) early_done_ = true;
+      runs_++;
+      return;
+    }
+  }
+  run_msms_body(false);
+  runs_++;
+}
+
+void Prover::run_msms_body(bool capturing) {
   // empty shards write nothing: start every proof from infinity (all-zero XYZZ)
   G16_CUDA(cudaMemsetAsync(results_.p, 0, sizeof(MsmResults), main_));
   // ev_[0]: witness ready on main_; every worker stream waits for it
@@ -960,13 +1012,13 @@ void Prover::run_msms(g16_stats* stats) {
   if (masked_partials_) {
     // this shard's share of s ** pi_a + r ** rho, folded into its c1 partial while B2 / H are still in flight
     if (R->owns_ab) {
-      G16_CUDA(cudaStreamWaitEvent(tail_[2], ev_[23], 0));
+      if (!capturing) G16_CUDA(cudaStreamWaitEvent(tail_[2], ev_[23], 0));
       k_shard_early<<<1, 256, 0, tail_[2]>>>(results_.as<MsmResults>(), mask_.as<MaskTerms>(), early_.as<G1XYZZ>() + 1);
       G16_LAUNCH_CHECK();
     }
   } else if (mask_started_ && R->shard_count == 1) {
     // the MSM-dependent scalar multiplications start now and overlap with the B2 / H work still in flight
-    G16_CUDA(cudaStreamWaitEvent(tail_[2], ev_[23], 0));
+    if (!capturing) G16_CUDA(cudaStreamWaitEvent(tail_[2], ev_[23], 0));
     k_assemble_early<<<1, 256, 0, tail_[2]>>>(results_.as<MsmResults>(), mask_.as<MaskTerms>(), proof_.as<g16_proof>(),
                                             early_.as<G1XYZZ>(), early_.as<G1XYZZ>() + 1);
     G16_LAUNCH_CHECK();
@@ -978,12 +1030,16 @@ void Prover::run_msms(g16_stats* stats) {
     G16_CUDA(cudaStreamWaitEvent(main_, ev_[13 + i], 0));
   }
   G16_CUDA(cudaEventRecord(ev_[18], main_));
-  (void)stats;   // phase times are read by collect_stats() once the work has completed
 }
 
 // valid after the main stream has been synchronised past the events of the last run_msms()
 void Prover::collect_stats(g16_stats* stats) {
   if (!stats) return;
+  if (use_graph_ && runs_ >= 2) {         // the phase events live inside the replayed graph: only the totals are timed
+    cudaEventElapsedTime(&stats->ms_h2d, ev_[20], ev_[21]);
+    cudaGetLastError();
+    return;
+  }
   cudaEventElapsedTime(&stats->ms_abc, ev_[1], ev_[2]);
   cudaEventElapsedTime(&stats->ms_quotient, ev_[2], ev_[3]);
   cudaEventElapsedTime(&stats->ms_msm_h, ev_[3], ev_[4]);

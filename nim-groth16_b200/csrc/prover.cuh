@@ -108,6 +108,7 @@ class Prover {
   void witness_finish(int form, size_t h2d_bytes);
   const std::vector<std::pair<size_t, size_t>>& witness_needs() const { return R->witness_needs; }
   void run_msms(g16_stats* stats);                     // ABC, quotient, five MSMs -> results_ (asynchronous)
+  void run_msms_body(bool capturing);                  // the launches themselves (replayed from a CUDA graph when enabled)
   void collect_stats(g16_stats* stats);                // phase times of the last run (after completion)
   void partials_to_affine(void* partials_dev);         // results_ -> g16_partials (device), synchronous
   // ordering against a caller-owned stream (the collective between partials and finish): direction 0 makes
@@ -162,6 +163,11 @@ class Prover {
   cudaStream_t tail_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t tdone_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t h2d_bytes_ = 0;                // witness bytes copied by the last load_witness()
+  // CUDA graph of run_msms_body per mode (0: no mask kernel, 1: masked partials, 2: early assembly); opt-in G16_GRAPH=1
+  struct GraphSlot { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; bool failed = false; };
+  GraphSlot graphs_[3];
+  int use_graph_ = 0;
+  uint64_t runs_ = 0;
   cudaEvent_t tev_[2] = {nullptr, nullptr};
   ProofOut* proof_pinned_ = nullptr;
 };
