@@ -234,6 +234,10 @@ int g16_prove_finish_submit(g16_ctx* ctx, const void* gathered_partials_dev, int
  * g16_prove_partials_submit; direction 1 makes the context wait for everything enqueued on `stream` so far (the
  * all-gather) before g16_prove_finish_submit's kernels run. */
 int g16_ctx_order_stream(g16_ctx* ctx, void* stream, int direction);
+/* Which layout the context ended up with (1 = resident window tables, 0 = plain points: G16_ZKEY_ONE_SHOT, or the tables
+ * would not have fit the device -- environment G16_TABLE_BUDGET_MB overrides the budget of 80 % of the free memory) and
+ * how much device memory it holds (all devices of a multi-device context). */
+int g16_ctx_layout(g16_ctx* ctx, int* window_tables, uint64_t* device_bytes);
 /* bytes of witness the last g16_prove* / g16_prove_partials* call copied to this context's device(s) */
 int g16_ctx_last_witness_bytes(g16_ctx* ctx, uint64_t* bytes);
 /* the five MSM sums of the most recent g16_prove* call on this context, as affine records (diagnostics) */

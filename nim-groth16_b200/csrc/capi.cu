@@ -423,6 +423,14 @@ int g16_ctx_order_stream(g16_ctx* ctx, void* stream, int direction) {
     ctx->prover->order_stream(reinterpret_cast<cudaStream_t>(stream), direction);
   });
 }
+int g16_ctx_layout(g16_ctx* ctx, int* window_tables, uint64_t* device_bytes) {
+  return guard([&] {
+    G16_REQUIRE(ctx && (ctx->prover || ctx->multi), "context is null");
+    Prover& p = ctx->multi ? ctx->multi->shard(0) : *ctx->prover;
+    if (window_tables) *window_tables = p.table_layout() ? 1 : 0;
+    if (device_bytes) *device_bytes = ctx->multi ? ctx->multi->resident_bytes() : p.resident_bytes();
+  });
+}
 int g16_ctx_last_witness_bytes(g16_ctx* ctx, uint64_t* bytes) {
   return guard([&] {
     G16_REQUIRE(ctx && (ctx->prover || ctx->multi) && bytes, "null argument");

@@ -572,6 +572,23 @@ Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_
   n = (size_t)1 << log_n;
   precomp = !(zk.flags & G16_ZKEY_ONE_SHOT);
   if (const char* e = getenv("G16_LAYOUT")) precomp = e[0] != 'p';     // "plain" / "table": A/B runs
+  if (precomp) {
+    // The window tables are ~13x the points this context owns (5.2 GB at 2^20, 84 GB at 2^24 on one GPU).  When they
+    // do not fit the device -- next to the staging copies of the upload and the per-proof workspaces -- the context
+    // falls back to the plain layout (1x the key, proofs ~25 % slower) instead of failing.  G16_TABLE_BUDGET_MB
+    // overrides the budget (default: 80 % of the free device memory).
+    shard_plan(nvars, npubs, n, shard_index, shard_count, plan);
+    const double pts_g1 = (double)(plan.a1_hi - plan.a1_lo) + (double)(plan.b1_hi - plan.b1_lo) +
+                          (double)(plan.c1_hi - plan.c1_lo) + (double)(plan.h_hi - plan.h_lo);
+    const double pts_g2 = (double)(plan.b2_hi - plan.b2_lo);
+    const double need = (14.0 + 1.0) * (64.0 * pts_g1 + 128.0 * pts_g2)          // tables + staging copies
+                        + 2.0 * 16.0 * 14.0 * ((double)nvars + (double)n);      // sorter / bucket workspaces of two slots
+    size_t fr = 0, tot = 0;
+    double budget = 0.0;
+    if (const char* e = getenv("G16_TABLE_BUDGET_MB")) budget = atof(e) * 1048576.0;
+    else if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) budget = 0.8 * (double)fr + 0.0 * (double)tot;
+    if (budget > 0.0 && need > budget) precomp = false;
+  }
   const bool validate = !(zk.flags & G16_ZKEY_TRUSTED);
   cudaStream_t main_ = nullptr, copy_ = nullptr;
   G16_CUDA(cudaStreamCreateWithFlags(&main_, cudaStreamNonBlocking));

@@ -138,6 +138,7 @@ class Prover {
   size_t resident_bytes() const;
   size_t last_witness_bytes() const { return h2d_bytes_; }
   const ShardPlan& plan() const { return R->plan; }
+  bool table_layout() const { return R->precomp; }
 
  private:
   void init_slot();

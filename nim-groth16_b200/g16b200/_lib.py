@@ -89,6 +89,7 @@ SIGNATURES = {
     "g16_shard_plan": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "g16_ctx_order_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "g16_ctx_last_witness_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "g16_ctx_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "g16_ctx_set_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "g16_prove_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]),
     "g16_ctx_last_partials": (C.c_int, [C.c_void_p, C.c_void_p]),

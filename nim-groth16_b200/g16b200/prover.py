@@ -185,6 +185,12 @@ class ProverContext:
         self.last_stats = st.as_dict()
         return self.last_stats
 
+    def layout(self):
+        """(has_window_tables, device_bytes): g16_ctx_layout."""
+        t, b = C.c_int(), C.c_uint64()
+        _lib.check(_lib.load().g16_ctx_layout(self._h, C.byref(t), C.byref(b)))
+        return bool(t.value), int(b.value)
+
     def last_witness_bytes(self) -> int:
         """Bytes of witness the last prove / partials call copied to the device(s) of this context."""
         n = C.c_uint64()

@@ -330,3 +330,63 @@ def test_nccl_ranks_produce_the_ground_truth_proof(g, world, tmp_path):
     prf = ctx.prove(wit, g.Mask(bench.MASK_R, bench.MASK_S))
     ctx.close()
     assert res["proof"] == (prf.pi_a.tobytes() + prf.pi_b.tobytes() + prf.pi_c.tobytes()).hex()
+
+
+def test_tables_fall_back_to_plain_points_when_they_do_not_fit(g, monkeypatch):
+    """the resident tables are 13x the key; a key whose tables exceed the device budget gets the plain
+    layout instead of an allocation failure (G16_TABLE_BUDGET_MB forces the situation), same proof."""
+    zk, wit = _fixture(g, 9000)
+    m = g.Mask(o.Rng(21).fr(), o.Rng(22).fr())
+    a = g.ProverContext(zk)
+    assert a.layout()[0] is True
+    want = a.prove(wit, m)
+    big = a.layout()[1]
+    a.close()
+    monkeypatch.setenv("G16_TABLE_BUDGET_MB", "1")
+    b = g.ProverContext(zk)
+    assert b.layout()[0] is False
+    assert _same(b.prove(wit, m), want)
+    assert b.layout()[1] < big
+    b.close()
+
+
+def test_cuda_graph_mode_gives_the_same_proofs(g):
+    """G16_GRAPH=1 (opt-in): the per-proof DAG replayed as one CUDA graph from the second proof of a context slot on --
+    single context, clone, sharded contexts with masked records -- bit-identical proofs (run in a child process: the
+    switch is read when a context slot is created)."""
+    code = r'''
+import os, sys
+sys.path.insert(0, os.path.join(%(root)r, "nim-groth16_b200")); sys.path.insert(0, os.path.join(%(root)r, "oracle"))
+import numpy as np, torch
+import g16b200 as g, g16_oracle as o
+from g16b200 import encoding as e
+r1cs, wit = g.synthetic_chain_circuit(3000, seed=3)
+zk, _ = g.fake_circuit_setup(r1cs, g.ToxicWaste(11, 22, 33, 44, 55), 1)
+wit = np.ascontiguousarray(wit)
+masks = [g.Mask(o.Rng(k).fr(), o.Rng(k + 50).fr()) for k in range(4)]
+os.environ.pop("G16_GRAPH", None)
+ref = g.ProverContext(zk)
+want = [ref.prove(wit, m) for m in masks]
+ref.close()
+os.environ["G16_GRAPH"] = "1"
+c = g.ProverContext(zk)
+c2 = c.clone()
+for rep in range(2):
+    for ctx in (c, c2):
+        for m, w in zip(masks, want):
+            p = ctx.prove(wit, m)
+            assert np.array_equal(p.pi_a, w.pi_a) and np.array_equal(p.pi_b, w.pi_b) and np.array_equal(p.pi_c, w.pi_c)
+c.close(); c2.close()
+G = 3
+ctxs = [g.ProverContext(zk, k, G) for k in range(G)]
+parts = torch.zeros((G, g._lib.PARTIALS_BYTES), dtype=torch.uint8, device="cuda")
+for m, w in zip(masks, want):
+    for k, ctx in enumerate(ctxs):
+        ctx.set_mask(m)
+        ctx.prove_partials(wit.ctypes.data, e.FORM_STD, 0, parts[k].data_ptr())
+    raw = ctxs[0].prove_finish(parts.data_ptr(), G, m)
+    assert bytes(raw.pi_c) == w.pi_c.tobytes() and bytes(raw.pi_a) == w.pi_a.tobytes() and bytes(raw.pi_b) == w.pi_b.tobytes()
+print("graph ok")
+''' % {"root": ROOT}
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "graph ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -199,3 +199,28 @@ def test_bucket_reduction_plan_emulation(L):
         assert info[5] <= 4 and info[3] <= 20
         seen_level2 |= info[1] > 1
     assert seen_level2                      # the 2^19-bucket sets of the resident prover use level 2
+
+
+def test_lazy_fp2_multiplication_model_is_carry_exact():
+    """tools/emu_lazy_fp2.py: the instruction-level model of the lazily reduced Fp2 multiplication of field.cuh (wide
+    products on two column-parity accumulators, reduction-only Montgomery loop, Karatsuba on unreduced values) -- every
+    carry the PTX drops is asserted to be zero, results against Python integers, for both moduli and edge operands."""
+    import os, random, sys
+    tools = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")
+    sys.path.insert(0, tools)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        import emu_lazy_fp2 as m
+    rnd = random.Random(7)
+    for mod in (m.P, m.R):
+        inv = (-pow(mod, -1, 1 << 32)) % (1 << 32)
+        rinv = pow(1 << 256, -1, mod)
+        edge = [0, 1, mod - 1, mod - 2, (1 << 255) % mod, (1 << 224) - 1]
+        for t in range(300):
+            pick = (lambda: rnd.choice(edge)) if t < 100 else (lambda: rnd.randrange(mod))
+            a0, a1, b0, b1 = pick(), pick(), pick(), pick()
+            c0, c1 = m.fp2_mul_lazy(a0, a1, b0, b1, mod, inv)
+            assert c0 == (a0 * b0 - a1 * b1) * rinv % mod and c1 == (a0 * b1 + a1 * b0) * rinv % mod
+            x = rnd.randrange(mod << 256) if t >= 100 else rnd.choice([0, (mod << 256) - 1, (1 << 256) - 1, 1 << 256])
+            assert m.redc(m.limbs(x, 16), mod, inv) == x * rinv % mod
+        m.mul_wide((1 << 256) - 1, (1 << 256) - 1)
