@@ -586,7 +586,19 @@ Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_
     size_t fr = 0, tot = 0;
     double budget = 0.0;
     if (const char* e = getenv("G16_TABLE_BUDGET_MB")) budget = atof(e) * 1048576.0;
-    else if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) budget = 0.8 * (double)fr + 0.0 * (double)tot;
+    else if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+      // memory cached by the library's pool (freed by earlier contexts) is available to this one as well
+      double cached = 0.0;
+      int dev = 0;
+      cudaMemPool_t pool = nullptr;
+      uint64_t reserved = 0, used = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess &&
+          cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+          cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+        cached = (double)(reserved - used);
+      cudaGetLastError();
+      budget = 0.8 * ((double)fr + cached);
+    }
     if (budget > 0.0 && need > budget) precomp = false;
   }
   const bool validate = !(zk.flags & G16_ZKEY_TRUSTED);
