@@ -14,28 +14,22 @@ MultiProver::MultiProver(const g16_zkey_view& zk, const std::vector<int>& device
   int have = 0;
   G16_CUDA(cudaGetDeviceCount(&have));
   for (int d : dev_) G16_REQUIRE(d >= 0 && d < have, "multi-device context: no such device");
-  // NVLink peer access between the assembling device and the others (the witness may also live on any of them)
-  for (int k = 1; k < G; k++) {
-    if (dev_[k] == dev_[0]) continue;               // the same device listed twice: a test configuration
-    int can = 0;
-    cudaDeviceCanAccessPeer(&can, dev_[0], dev_[k]);
-    if (!can) continue;                             // peer copies are then staged through the host by the runtime
-    {
-      DeviceGuard g(dev_[0]);
-      cudaError_t e = cudaDeviceEnablePeerAccess(dev_[k], 0);
-      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) G16_CUDA(e);
-      cudaGetLastError();
-    }
-    {
-      DeviceGuard g(dev_[k]);
-      cudaError_t e = cudaDeviceEnablePeerAccess(dev_[0], 0);
-      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) G16_CUDA(e);
-      cudaGetLastError();
-    }
-    // DevBuf memory comes from the stream-ordered pools: make them peer-accessible as well (NVLink copies of the
-    // records and of a device-resident witness instead of copies staged through the host)
-    for (int a = 0; a < 2; a++) {
-      const int owner = a ? dev_[0] : dev_[k], peer = a ? dev_[k] : dev_[0];
+  // NVLink peer access between every pair of devices: the partial records go to the first device, the witness
+  // slices go from every device to every device that reads them.  DevBuf memory comes from the stream-ordered pools,
+  // which need their own access grant (without it the runtime stages peer copies through the host).
+  for (int a = 0; a < G; a++)
+    for (int b2 = 0; b2 < G; b2++) {
+      const int owner = dev_[a], peer = dev_[b2];
+      if (owner == peer) continue;                  // the same device listed twice: a test configuration
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, peer, owner);
+      if (!can) continue;                           // peer copies are then staged through the host by the runtime
+      {
+        DeviceGuard g(peer);                        // `peer` maps the memory of `owner`
+        cudaError_t e = cudaDeviceEnablePeerAccess(owner, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) G16_CUDA(e);
+        cudaGetLastError();
+      }
       cudaMemPool_t pool = nullptr;
       if (cudaDeviceGetDefaultMemPool(&pool, owner) != cudaSuccess) continue;
       cudaMemAccessDesc d;
@@ -45,7 +39,6 @@ MultiProver::MultiProver(const g16_zkey_view& zk, const std::vector<int>& device
       d.flags = cudaMemAccessFlagsProtReadWrite;
       if (cudaMemPoolSetAccess(pool, &d, 1) != cudaSuccess) cudaGetLastError();
     }
-  }
   for (int k = 0; k < G; k++) {
     DeviceGuard g(dev_[k]);
     shard_.emplace_back(new Prover(zk, k, G));
