@@ -252,6 +252,8 @@ def run_ours(args):
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # a second communicator for the witness all-gather of the scatter upload mode (see ShardedProver.partials_submit_host)
+    wgroup = dist.new_group() if dist is not None else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -309,7 +311,7 @@ def run_ours(args):
                     if i >= dd:
                         last = sp.wait()
                     if mem_kind == MEM_HOST and scatter_mode[0]:
-                        sp.partials_submit_host(w_pinned_rows, mask)
+                        sp.partials_submit_host(w_pinned_rows, mask, group=wgroup)
                     else:
                         sp.partials_submit(ptr, mem_kind, mask)
                     sp.exchange_submit(mask)

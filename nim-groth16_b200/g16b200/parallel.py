@@ -78,7 +78,11 @@ class ShardedProver:
         rank uploads the rank-th of `world` slices over its own link, the slices are all-gathered over NVLink (NCCL), and
         the partial sums read the gathered device copy -- instead of every rank pulling the intervals it needs (up to
         the whole witness) through the host's PCIe lanes at the same time.  Ordered on the device like
-        exchange_submit(): no host synchronisation."""
+        exchange_submit(): no host synchronisation.
+
+        `group`: give this all-gather its OWN process group (dist.new_group()).  Collectives of one group execute in
+        issue order on one NCCL stream; the record all-gather of the previous proof waits for that proof's MSMs, so on
+        the same group the witness of the next proof would queue behind it and the proofs would no longer overlap."""
         import torch
         import torch.distributed as dist
         lib = _lib.load()
@@ -86,14 +90,15 @@ class ShardedProver:
         per = -(-n // self.world)
         if getattr(self, "_wbuf", None) is None or self._wbuf.shape[0] != per * self.world:
             self._wbuf = torch.zeros((per * self.world, 4), dtype=torch.int64, device=self.device)
+            self._wstream = torch.cuda.Stream(device=self.device)
         lo, hi = min(n, per * self.rank), min(n, per * (self.rank + 1))
         mine = self._wbuf[per * self.rank: per * (self.rank + 1)]
-        if hi > lo:
-            mine[: hi - lo].copy_(witness_pinned[lo:hi], non_blocking=True)
-        if self.world > 1:
-            dist.all_gather_into_tensor(self._wbuf.view(-1), mine.reshape(-1), group=group)
-        st = torch.cuda.current_stream(self.device)
-        _lib.check(lib.g16_ctx_order_stream(self.ctx._h, st.cuda_stream, 1))     # the context waits for the gather
+        with torch.cuda.stream(self._wstream):                  # not the stream the record all-gathers are ordered on
+            if hi > lo:
+                mine[: hi - lo].copy_(witness_pinned[lo:hi], non_blocking=True)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self._wbuf.view(-1), mine.reshape(-1), group=group)
+        _lib.check(lib.g16_ctx_order_stream(self.ctx._h, self._wstream.cuda_stream, 1))   # the context waits for the gather
         self.h2d_bytes = (hi - lo) * 32
         self.partials_submit(self._wbuf.data_ptr(), MEM_DEVICE, mask)
 

@@ -287,9 +287,10 @@ sp = g.parallel.ShardedProver(zk, rank, world, device=local)
 w = np.ascontiguousarray(wit)
 outs = []
 wp = torch.from_numpy(w.view(np.int64).copy()).pin_memory()
+wgroup = dist.new_group()
 for it in range(3):
     if it == 1:                       # the witness uploaded once in `world` slices and all-gathered over NVLink
-        sp.partials_submit_host(wp, mask)
+        sp.partials_submit_host(wp, mask, group=wgroup)
     else:
         sp.partials_submit(w.ctypes.data, MEM_HOST, mask)
     raw = sp.complete(mask)
