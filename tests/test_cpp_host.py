@@ -160,6 +160,11 @@ def test_cli_multi_gpu_reproduces_the_golden_proof(exe, files, kat, gpus):
                        timeout=600, env=env)
     assert r.returncode == 0, r.stderr
     assert open(out).read() == open(one).read() and open(io).read() == open(io1).read()
+    # the mmap'ed zkey page-locked for the upload (g16_host_register; falls back silently where the platform refuses)
+    r = subprocess.run([exe] + args + ["-o", out, "-i", io], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, G16_PIN_ZKEY="1"))
+    assert r.returncode == 0, r.stderr
+    assert open(out).read() == open(one).read()
     # and through the environment alone (the Nim shim's route: nothing but G16_NGPUS changes)
     env2 = dict(env, G16_NGPUS=str(gpus))
     r = subprocess.run([exe] + args + ["-o", out, "-i", io], capture_output=True, text=True, timeout=600, env=env2)
