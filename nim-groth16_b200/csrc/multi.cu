@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <exception>
+#include <functional>
 #include <thread>
 
 namespace g16 {
@@ -90,8 +91,6 @@ void MultiProver::submit(const void* witness, int form, int mem_kind, const uint
   const int G = (int)dev_.size();
   G16_REQUIRE(!in_flight(), "a proof is already in flight on this context");
   PartialsAffine* all = gathered_.as<PartialsAffine>();
-  // one host thread per device enqueues that shard's proof (about 70 launches each): eight devices are fed in the
-  // time of one.  The calling thread takes the first device and joins the others before the finish is enqueued.
   // A host witness travels ONCE over PCIe: device k uploads the k-th of G slices over its own link, then every device
   // pulls the parts of the intervals it reads from the devices that hold them (NVLink peer copies ordered by events)
   // -- instead of up to G copies of the whole witness competing for the host's PCIe lanes.
@@ -101,15 +100,39 @@ void MultiProver::submit(const void* witness, int form, int mem_kind, const uint
     lo = nv * (size_t)k / (size_t)G;
     hi = k == G - 1 ? nv : nv * (size_t)(k + 1) / (size_t)G;
   };
+  auto run_on_all = [&](const std::function<void(int)>& fn) {
+    // one host thread per device (the calling thread takes the first) enqueues that device's part -- about 70
+    // launches per proof each: eight devices are fed in the time of one
+    std::vector<std::thread> workers;
+    std::vector<std::exception_ptr> errors((size_t)G);
+    for (int k = G - 1; k >= 1; k--)      // the devices with the G2 work (the longest kernels) are the last of the plan
+      workers.emplace_back([&, k] {
+        try {
+          fn(k);
+        } catch (...) {
+          errors[(size_t)k] = std::current_exception();
+        }
+      });
+    try {
+      fn(0);
+    } catch (...) {
+      errors[0] = std::current_exception();
+    }
+    for (auto& w : workers) w.join();
+    for (auto& e : errors)
+      if (e) std::rethrow_exception(e);
+  };
   if (scatter) {
     G16_REQUIRE(witness != nullptr, "witness is null");
-    for (int k = 0; k < G; k++) {
+    // phase 1: every device uploads its slice (a pageable source is staged by the calling thread, so the slices are
+    // staged in parallel as well); the peer copies of phase 2 need these events to have been recorded
+    run_on_all([&](int k) {
       DeviceGuard g(dev_[k]);
       size_t lo, hi;
       slice(k, lo, hi);
       shard_[k]->witness_begin(form);
       shard_[k]->witness_upload(witness, form, lo, hi);
-    }
+    });
   }
   auto enqueue = [&](int k) {
     DeviceGuard g(dev_[k]);
@@ -139,24 +162,7 @@ void MultiProver::submit(const void* witness, int form, int mem_kind, const uint
     G16_CUDA(cudaMemcpyPeerAsync(all + k, dev_[0], local_[k]->p, dev_[k], sizeof(PartialsAffine), p.main_stream()));
     G16_CUDA(cudaEventRecord(sent_[k], p.main_stream()));
   };
-  std::vector<std::thread> workers;
-  std::vector<std::exception_ptr> errors((size_t)G);
-  for (int k = G - 1; k >= 1; k--)        // the devices with the G2 work (the longest kernels) are the last of the plan
-    workers.emplace_back([&, k] {
-      try {
-        enqueue(k);
-      } catch (...) {
-        errors[(size_t)k] = std::current_exception();
-      }
-    });
-  try {
-    enqueue(0);
-  } catch (...) {
-    errors[0] = std::current_exception();
-  }
-  for (auto& w : workers) w.join();
-  for (auto& e : errors)
-    if (e) std::rethrow_exception(e);
+  run_on_all(enqueue);
   DeviceGuard g(dev_[0]);
   Prover& head = *shard_[0];
   for (int k = 1; k < G; k++) G16_CUDA(cudaStreamWaitEvent(head.main_stream(), sent_[k], 0));

@@ -602,11 +602,27 @@ Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_
     if (budget > 0.0 && need > budget) precomp = false;
   }
   const bool validate = !(zk.flags & G16_ZKEY_TRUSTED);
-  cudaStream_t main_ = nullptr, copy_ = nullptr;
-  G16_CUDA(cudaStreamCreateWithFlags(&main_, cudaStreamNonBlocking));
-  G16_CUDA(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking));
-  cudaEvent_t copied[6];
-  for (auto& e : copied) G16_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  struct Scoped {                       // streams and events of the build, released on every exit path
+    cudaStream_t main = nullptr, copy = nullptr;
+    cudaEvent_t copied[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~Scoped() {
+      if (main) {
+        cudaStreamSynchronize(main);
+        cudaStreamDestroy(main);
+      }
+      if (copy) {
+        cudaStreamSynchronize(copy);
+        cudaStreamDestroy(copy);
+      }
+      for (auto& e : copied)
+        if (e) cudaEventDestroy(e);
+    }
+  } sc;
+  G16_CUDA(cudaStreamCreateWithFlags(&sc.main, cudaStreamNonBlocking));
+  G16_CUDA(cudaStreamCreateWithFlags(&sc.copy, cudaStreamNonBlocking));
+  for (auto& e : sc.copied) G16_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  cudaStream_t main_ = sc.main, copy_ = sc.copy;
+  cudaEvent_t* copied = sc.copied;
   int ncopied = 0;
   shard_plan(nvars, npubs, n, shard_index, shard_count, plan);
 
@@ -643,9 +659,9 @@ Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_
   const size_t nh = plan.h_hi - plan.h_lo;
   if (nh) gh = msm_geometry(nh, msm_pick_window(nh, precomp), precomp);
 
-  // uploads, validation and table building; one raw staging buffer per array so that the copies of the next array
-  // overlap with the table kernel of the previous one (the copies are ordered on the same stream, the buffers
-  // are released at the end)
+  // uploads, validation and table building; one raw staging buffer per array and the copies on their own stream, so
+  // that the H2D of the next array overlaps with the table kernel of the previous one (the buffers are released at
+  // the end)
   std::vector<TableJob> jobs;
   DevBuf bad;
   bad.ensure(8 * 4);
@@ -730,9 +746,6 @@ Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_
   uint32_t bad_host[8];
   G16_CUDA(cudaMemcpyAsync(bad_host, bad.p, sizeof(bad_host), cudaMemcpyDeviceToHost, main_));
   G16_CUDA(cudaStreamSynchronize(main_));
-  cudaStreamDestroy(main_);
-  cudaStreamDestroy(copy_);
-  for (auto& e : copied) cudaEventDestroy(e);
   for (const TableJob& j : jobs) {
     const uint32_t idx = bad_host[j.bad_dev - bad.as<uint32_t>()];
     // curves.nim:95-107 mkG1 / mkG2 assert texts
