@@ -330,6 +330,11 @@ int g16_selftest(uint32_t seed, uint32_t cases);
  * Instruction-mix models (multiplies/s): 10 = 128 IMAD.WIDE + 40 IADD3 (today's fmul), 11 = 112 + 152, 12 = 112 + 200.
  * 13 = Montgomery multiplies without the final conditional subtraction (operands and results in [0, 2p)). */
 int g16_bench_int_pipe(int kind, double* ops_per_sec, float* ms);
+/* GLV split of a scalar k < r (standard form): k = (+-k1) + (+-k2) * lambda (mod r), both magnitudes below 2^127,
+ * lambda = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd the eigenvalue of (x, y) -> (beta x, y) on G1.  What the
+ * prover does with the blinding scalars before s ** pi_A and r ** rho (prover.nim:298-299, csrc/glv.h); exported so that
+ * the host arithmetic is testable without a device. */
+int g16_glv_decompose(const uint64_t k_std[4], uint64_t k1_abs[2], uint64_t k2_abs[2], int* neg1, int* neg2);
 /* number of kernels this library has launched in this process */
 uint64_t g16_kernel_launch_count(void);
 

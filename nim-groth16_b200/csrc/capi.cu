@@ -14,6 +14,7 @@
 #include "ntt.cuh"
 #include "prover.cuh"
 #include "multi.cuh"
+#include "glv.h"
 #include <stdlib.h>
 
 namespace g16 {
@@ -229,6 +230,26 @@ int g16_release_cached_memory(void) {
     }
     cudaSetDevice(cur);
   });
+}
+int g16_glv_decompose(const uint64_t k_std[4], uint64_t k1_abs[2], uint64_t k2_abs[2], int* neg1, int* neg2) {
+  // pure host arithmetic: no device needed, so no guard()
+  if (!k_std || !k1_abs || !k2_abs || !neg1 || !neg2) {
+    set_last_error("g16_glv_decompose: null argument");
+    return G16_ERR_ARG;
+  }
+  bool ok = false;
+  GlvSplit sp = glv_decompose(k_std, &ok);
+  k1_abs[0] = sp.k1[0];
+  k1_abs[1] = sp.k1[1];
+  k2_abs[0] = sp.k2[0];
+  k2_abs[1] = sp.k2[1];
+  *neg1 = (int)sp.neg1;
+  *neg2 = (int)sp.neg2;
+  if (!ok) {
+    set_last_error("g16_glv_decompose: scalar out of range");
+    return G16_ERR_ARG;
+  }
+  return G16_OK;
 }
 int g16_host_register(const void* ptr, size_t bytes) {
   return guard([&] {

@@ -15,6 +15,7 @@
 #include <string.h>
 #include <algorithm>
 #include "ntt.cuh"
+#include "glv.h"
 
 namespace g16 {
 
@@ -139,30 +140,46 @@ __global__ void __launch_bounds__(256) k_mask_terms(const SpecPointsDev* spec, c
 // The two scalar multiplications do not walk a double-and-add chain of ~380 dependent point operations: one
 // thread per half writes the 254 doublings 2^i P into a scratch table, then 128 threads add the entries selected
 // by the scalar's bits in a tree (same scheme as the delta tables of k_mask_terms).  256 threads = 2 halves.
-__global__ void __launch_bounds__(256) k_assemble_early(const MsmResults* res, const MaskTerms* m, g16_proof* proof,
-                                                        G1XYZZ* partial_c, G1XYZZ* scratch) {
-  __shared__ G1XYZZ red[256];
-  const uint32_t h = threadIdx.x >> 7, j = threadIdx.x & 127u;
-  G1XYZZ* tbl = scratch + h * 256;
-  if (j == 0) {
-    G1XYZZ t;
-    if (h == 0) xyzz_add_ni(t, ldv(&m->t_a), ldv(&res->a1));        // pi_a                 prover.nim:282
-    else xyzz_add_ni(t, ldv(&m->t_b1), ldv(&res->b1));              // rho                  prover.nim:288
-    G1Affine pa;
-    xyzz_to_affine_ni(pa, t);
-    if (h == 0) stv(reinterpret_cast<G1Affine*>(proof->pi_a), pa);
-    G1XYZZ p = xyzz_from_affine(pa);
-    for (int i = 0; i < 256; i++) {
+// k * P for the two witness-dependent products of a proof, 128 threads per product (h = which half of the block):
+// one thread writes the doublings 2^i P into `tbl`, then every thread adds the entries its scalar bits select and a
+// tree sums the 128 partial results.  With the GLV split k = k1 + k2 lambda, |k_i| < 2^127 (glv.h), the table needs 127
+// instead of 254 SEQUENTIAL doublings -- the latency of this kernel -- and thread j adds (+-) 2^j P for bit j of k1 and
+// (+-) phi(2^j P) = (beta X, Y, ZZ, ZZZ) for bit j of k2.  Returns the sum in thread 0 of the half (red[h * 128]).
+static __device__ void glv_scalar_mul_half(const G1XYZZ& base, bool base_ready_in_thread0, const uint32_t* k256,
+                                           const uint32_t* glv, bool glv_ok, G1XYZZ* tbl, G1XYZZ* red, G1XYZZ& out) {
+  const uint32_t j = threadIdx.x & 127u;
+  const int ndbl = glv_ok ? 128 : 256;
+  if (j == 0 && base_ready_in_thread0) {
+    G1XYZZ p = base;
+    for (int i = 0; i < ndbl; i++) {
       stv(tbl + i, p);
-      if (i < 255) xyzz_dbl_ni(p, p);
+      if (i < ndbl - 1) xyzz_dbl_ni(p, p);
     }
   }
   __syncthreads();
-  const uint32_t* k = h == 0 ? m->s : m->r;                         // s ** pi_a, r ** rho  prover.nim:298,299
   G1XYZZ acc = xyzz_inf<Fp>();
-  if ((k[j >> 5] >> (j & 31)) & 1u) acc = ldv(tbl + j);
-  const uint32_t j2 = j + 128;
-  if ((k[j2 >> 5] >> (j2 & 31)) & 1u) xyzz_add_ni(acc, acc, ldv(tbl + j2));
+  if (glv_ok) {
+    if ((glv[j >> 5] >> (j & 31)) & 1u) {
+      acc = ldv(tbl + j);
+      if (glv[8]) acc.y = fneg(acc.y);
+    }
+    if ((glv[4 + (j >> 5)] >> (j & 31)) & 1u) {
+      // beta = 0x59e26bcea0d48bacd4f263f1acdb5c4f5763473177fffffe: the cube root of unity with phi(P) = lambda P
+      Fp beta;
+      const uint32_t bw[8] = {0x77fffffeu, 0x57634731u, 0xacdb5c4fu, 0xd4f263f1u, 0xa0d48bacu, 0x59e26bceu, 0u, 0u};
+#pragma unroll
+      for (int i = 0; i < 8; i++) beta.v[i] = bw[i];
+      beta = to_mont(beta);
+      G1XYZZ t = ldv(tbl + j);
+      t.x = fmul(t.x, beta);
+      if (glv[9]) t.y = fneg(t.y);
+      xyzz_add_ni(acc, acc, t);
+    }
+  } else {
+    if ((k256[j >> 5] >> (j & 31)) & 1u) acc = ldv(tbl + j);
+    const uint32_t j2 = j + 128;
+    if ((k256[j2 >> 5] >> (j2 & 31)) & 1u) xyzz_add_ni(acc, acc, ldv(tbl + j2));
+  }
   red[threadIdx.x] = acc;
   __syncthreads();
   for (uint32_t st = 64; st > 0; st >>= 1) {
@@ -173,6 +190,26 @@ __global__ void __launch_bounds__(256) k_assemble_early(const MsmResults* res, c
     }
     __syncthreads();
   }
+  out = acc;
+}
+
+__global__ void __launch_bounds__(256) k_assemble_early(const MsmResults* res, const MaskTerms* m, g16_proof* proof,
+                                                        G1XYZZ* partial_c, G1XYZZ* scratch) {
+  __shared__ G1XYZZ red[256];
+  const uint32_t h = threadIdx.x >> 7, j = threadIdx.x & 127u;
+  G1XYZZ base = xyzz_inf<Fp>();
+  if (j == 0) {
+    G1XYZZ t;
+    if (h == 0) xyzz_add_ni(t, ldv(&m->t_a), ldv(&res->a1));        // pi_a                 prover.nim:282
+    else xyzz_add_ni(t, ldv(&m->t_b1), ldv(&res->b1));              // rho                  prover.nim:288
+    G1Affine pa;
+    xyzz_to_affine_ni(pa, t);
+    if (h == 0) stv(reinterpret_cast<G1Affine*>(proof->pi_a), pa);
+    base = xyzz_from_affine(pa);
+  }
+  G1XYZZ acc;                                                       // s ** pi_a, r ** rho  prover.nim:298,299
+  glv_scalar_mul_half(base, true, h == 0 ? m->s : m->r, m->glv[h == 0 ? 1 : 0], m->glv_ok != 0, scratch + h * 256, red,
+                      acc);
   if (threadIdx.x == 0) {                             // + negFr(r*s) ** delta1 + MSM(zs, C1)   prover.nim:300,302
     G1XYZZ t;
     xyzz_add_ni(t, acc, red[128]);
@@ -208,30 +245,11 @@ __global__ void __launch_bounds__(64) k_assemble_final(const MsmResults* res, co
 __global__ void __launch_bounds__(256) k_shard_early(MsmResults* res, const MaskTerms* m, G1XYZZ* scratch) {
   __shared__ G1XYZZ red[256];
   const uint32_t h = threadIdx.x >> 7, j = threadIdx.x & 127u;
-  G1XYZZ* tbl = scratch + h * 256;
-  if (j == 0) {
-    G1XYZZ p = ldv(h == 0 ? &res->a1 : &res->b1);
-    for (int i = 0; i < 256; i++) {
-      stv(tbl + i, p);
-      if (i < 255) xyzz_dbl_ni(p, p);
-    }
-  }
-  __syncthreads();
-  const uint32_t* k = h == 0 ? m->s : m->r;
-  G1XYZZ acc = xyzz_inf<Fp>();
-  if ((k[j >> 5] >> (j & 31)) & 1u) acc = ldv(tbl + j);
-  const uint32_t j2 = j + 128;
-  if ((k[j2 >> 5] >> (j2 & 31)) & 1u) xyzz_add_ni(acc, acc, ldv(tbl + j2));
-  red[threadIdx.x] = acc;
-  __syncthreads();
-  for (uint32_t st = 64; st > 0; st >>= 1) {
-    if (j < st) {
-      G1XYZZ o = red[threadIdx.x + st];
-      xyzz_add_ni(acc, acc, o);
-      red[threadIdx.x] = acc;
-    }
-    __syncthreads();
-  }
+  G1XYZZ base = xyzz_inf<Fp>();
+  if (j == 0) base = ldv(h == 0 ? &res->a1 : &res->b1);
+  G1XYZZ acc;
+  glv_scalar_mul_half(base, true, h == 0 ? m->s : m->r, m->glv[h == 0 ? 1 : 0], m->glv_ok != 0, scratch + h * 256, red,
+                      acc);
   if (threadIdx.x == 0) {
     G1XYZZ t;
     xyzz_add_ni(t, acc, red[128]);
@@ -1125,10 +1143,30 @@ void Prover::sum_partials(const void* gathered_dev, int count) {
 void Prover::start_mask(const uint64_t r[4], const uint64_t s[4]) {
   G16_REQUIRE(r != nullptr && s != nullptr, "mask is null");
   MaskTerms* m = mask_.as<MaskTerms>();
-  uint32_t rs[16];
+  uint32_t rs[16 + 20 + 4];                            // r, s, glv[2][10], glv_ok + padding: contiguous in MaskTerms
   memcpy(rs, r, 32);
   memcpy(rs + 8, s, 32);
-  G16_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(m) + offsetof(MaskTerms, r), rs, 64, cudaMemcpyHostToDevice,
+  bool ok_r = false, ok_s = false;
+  const GlvSplit gr = glv_decompose(r, &ok_r), gs = glv_decompose(s, &ok_s);
+  const GlvSplit* sp[2] = {&gr, &gs};
+  for (int i = 0; i < 2; i++) {
+    uint32_t* g = rs + 16 + 10 * i;
+    memcpy(g, sp[i]->k1, 16);
+    memcpy(g + 4, sp[i]->k2, 16);
+    g[8] = sp[i]->neg1;
+    g[9] = sp[i]->neg2;
+  }
+  static int glv_on = -1;
+  if (glv_on < 0) {
+    const char* e = getenv("G16_GLV");                 // A/B knob: 0 = plain 254-step doubling chains
+    glv_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  rs[36] = (glv_on && ok_r && ok_s) ? 1u : 0u;
+  rs[37] = rs[38] = rs[39] = 0;
+  static_assert(offsetof(MaskTerms, glv) == offsetof(MaskTerms, r) + 64 &&
+                    offsetof(MaskTerms, glv_ok) == offsetof(MaskTerms, r) + 64 + 80,
+                "MaskTerms: r, s, glv, glv_ok must be contiguous");
+  G16_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(m) + offsetof(MaskTerms, r), rs, sizeof(rs), cudaMemcpyHostToDevice,
                            st_mask_));
   k_mask_terms<<<6, 256, 256 * sizeof(G2XYZZ), st_mask_>>>(R->spec.as<SpecPointsDev>(), R->dtab1.as<G1XYZZ>(),
                                                            R->dtab2.as<G2XYZZ>(), R->atab1.as<G1XYZZ>(),

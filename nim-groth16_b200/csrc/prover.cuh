@@ -37,6 +37,10 @@ struct alignas(16) MaskTerms {        // prover.nim:279-300, everything that doe
   G1XYZZ t_sa;   // s * alpha1     (masked partials only, see Prover::set_mask)
   G1XYZZ t_rb;   // r * beta1
   uint32_t r[8], s[8];
+  // GLV split of r ([0]) and s ([1]) (csrc/glv.h): |k1| in words 0..3, |k2| in 4..7, their signs in 8, 9; glv_ok = 0
+  // sends the witness-dependent scalar multiplications down the plain 256-bit path
+  uint32_t glv[2][10];
+  uint32_t glv_ok, pad_[3];
 };
 
 struct alignas(16) SpecPointsDev {    // SpecPoints (zkey_types.nim:24-31) needed by the prover

@@ -115,6 +115,7 @@ SIGNATURES = {
     "g16_fixed_base_g2": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "g16_selftest": (C.c_int, [C.c_uint32, C.c_uint32]),
     "g16_bench_int_pipe": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+    "g16_glv_decompose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "g16_kernel_launch_count": (C.c_uint64, []),
 }
 
