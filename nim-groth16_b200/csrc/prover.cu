@@ -11,9 +11,11 @@
 // the point range [N*k/G, N*(k+1)/G) of every MSM (msm.nim:107-115): run_msms() then yields partial sums
 // that the host side all-gathers between GPUs.
 #include "prover.cuh"
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <mutex>
 #include "ntt.cuh"
 #include "glv.h"
 
@@ -345,11 +347,14 @@ __global__ void __launch_bounds__(160) k_sum_partials(const PartialsAffine* part
 // every rank run all five MSMs on a G-times smaller input: five bucket-set reductions, five latency-bound tails and
 // a smaller window (more pairs per point) on every rank -- the fixed costs that capped 8-GPU efficiency at 0.55.
 // The default policy "line" therefore places the MSMs themselves: the work of one proof is laid
-// on a line  [H | A1 | B1 | C1 | B2]  weighted by a cost model, and rank k owns the k-th segment, i.e. whole MSMs
-// plus at most a tail of one array and a head of another.  buildABC and the quotient cannot be split by points, so
-// every rank that owns H points computes them; the number m of such ranks is the one that minimises the modelled
-// load of the slowest rank.  Environment G16_SHARD_POLICY: "line" (default), "uniform" (the reference's equal
-// chunks of every array), "g2own" (BASELINE.json configs[3]: the G2 MSM alone on the last rank, the rest as "line").
+// on a line, e.g.  [H | A1 | B1 | C1 | B2], and rank k owns the k-th segment, i.e. whole MSMs plus at most a tail of
+// one array and a head of another.  buildABC and the quotient cannot be split by points, so every rank that owns H
+// points computes them.  The planner tries a handful of line orders and every number m of H ranks, cuts each
+// candidate so that no rank costs more than a bound L (bisection on L), and keeps the plan whose slowest rank is
+// cheapest according to `rank_cost`, a model fitted to measured busy times of single shard shapes
+// (tools/shape_probe.py, tools/fit_shard_model.py, profiles/r2_v9_shape_probe.log).
+// Environment G16_SHARD_POLICY: "line" (default), "uniform" (the reference's equal chunks of every array), "g2own"
+// (BASELINE.json configs[3]: the G2 MSM alone on the last rank, the rest as "line").
 // Every rank evaluates the same arithmetic, so the plan needs no communication.
 // ---------------------------------------------------------------------------------------
 static void shard_range(size_t N, int k, int G, size_t& lo, size_t& hi) {   // msm.nim:107-111
@@ -357,27 +362,54 @@ static void shard_range(size_t N, int k, int G, size_t& lo, size_t& hi) {   // m
   hi = (k == G - 1) ? N : (N * (size_t)(k + 1)) / (size_t)G;
 }
 
-// Cost model in units of one 254-bit Montgomery multiplication at the measured peak rate (6.76e10 /s on a B200 --
-// only ratios matter).  Efficiencies are the measured fractions of that peak: G1 accumulate 0.95, G2
-// 0.82, bucket reduction 0.8, NTT passes 0.7; a sorted pair costs 2.2 (CUB radix sort, HBM-bound).
-static double msm_cost(size_t npts, bool g2) {
-  if (!npts) return 0.0;
-  const int c = msm_pick_window(npts, true);
-  const double W = (double)msm_num_windows(c), nb = (double)((size_t)1 << (c - 1));
-  const double acc = (double)npts * W * (g2 ? 28.0 / 0.82 : 10.0 / 0.95);
-  // bucket reduction: the throughput-bound level (2.1 additions per bucket, measured 0.27 ms in G1 and 1.1 ms in G2
-  // for 2^19 buckets) and the latency-bound levels behind it (0.43 / 1.4 ms), half of which hides behind the next
-  // proof in flight
-  const double red = nb * (g2 ? 113.0 : 30.0) / 0.8;
-  const double sort = (double)npts * W * 2.2 * (g2 ? 0.25 : 1.0);       // B2 shares the witness sort when co-located
-  const double tail = g2 ? 48.0e6 : 14.5e6;
-  return acc + red + sort + tail;
-}
-static double quotient_cost(size_t n, size_t nvars) {
-  const double lg = (double)ceil_log2_sz(n);
-  const double ntt = 3.0 * ((double)n * lg + (double)n) + 2.0 * (double)n;   // 6 NTTs + scaling + pointwise
-  const double abc = 4.0 * (double)n + (double)nvars;                        // nnz ~ 3n products + Cz
-  return (ntt + abc) / 0.7;
+// Busy time of one rank with two proofs in flight, in units of one 254-bit Montgomery multiplication at the measured
+// peak rate (6.76e10 /s on a B200 -- only ratios matter).  Least-squares fit to 30 shard shapes at 2^20 (rms error
+// 0.09 ms, worst 4.7 %): a sorted pair costs 1.24, an accumulated pair 10.3 (G1, 10 multiplications at 0.97 of peak)
+// or 30.7 (G2), a reduced bucket 24 / 84.5; every rank pays a fixed 0.46 ms of latency-bound tails once (they hide
+// behind the rank's other work, so a second group adds only 0.05 ms), the quotient runs at 0.79 of the modmul peak,
+// the witness-dependent scalar multiplications of a rank that owns A1 or B1 points cost 0.21 ms, a G2 bucket set
+// 0.22 ms, and a G2 MSM that shares the rank with G1 work of another range costs 0.6 ms extra.
+static double rank_cost(const ShardPlan& p, size_t nvars, size_t n) {
+  (void)nvars;
+  struct Grp { size_t lo, hi; int n1; bool g2; };
+  Grp grp[5];
+  int ng = 0;
+  const size_t r[4][2] = {{p.a1_lo, p.a1_hi}, {p.b1_lo, p.b1_hi}, {p.c1_lo, p.c1_hi}, {p.b2_lo, p.b2_hi}};
+  for (int a = 0; a < 4; a++) {
+    if (r[a][1] <= r[a][0]) continue;
+    int g = -1;
+    for (int i = 0; i < ng; i++)
+      if (grp[i].lo == r[a][0] && grp[i].hi == r[a][1]) g = i;
+    if (g < 0) {
+      g = ng++;
+      grp[g] = {r[a][0], r[a][1], 0, false};
+    }
+    if (a == 3) grp[g].g2 = true;
+    else grp[g].n1++;
+  }
+  const bool has_h = p.h_hi > p.h_lo, has_g2 = r[3][1] > r[3][0];
+  if (has_h) grp[ng++] = {p.h_lo, p.h_hi, 1, false};
+  if (!ng) return 0.0;
+  double cost = 33.4e6 + 17.6e6 * (ng - 1);
+  bool any_g1 = false;
+  for (int i = 0; i < ng; i++) {
+    const size_t npts = grp[i].hi - grp[i].lo;
+    const int c = msm_pick_window(npts, true);
+    const double pairs = (double)npts * (double)msm_num_windows(c), nb = (double)((size_t)1 << (c - 1));
+    cost += pairs * 0.95 + grp[i].n1 * (pairs * 10.9 + nb * 15.0);
+    if (grp[i].g2) cost += pairs * 31.4 + nb * 74.0;
+    if (grp[i].n1) any_g1 = true;
+  }
+  if (has_g2) cost += 11.5e6 + (any_g1 ? 27.6e6 : 0.0);
+  if (r[0][1] > r[0][0] || r[1][1] > r[1][0]) cost += 9.0e6;
+  if (has_h) {
+    const double lg = (double)ceil_log2_sz(n);
+    // 6 NTTs + scaling + pointwise at 0.89 of the modmul peak; buildABC gathers ~3n witness values:
+    // 0.085 ms at 2^20, where the witness stays in the 126 MB L2, 1.58 ms at 2^22, where it does not
+    cost += (3.0 * ((double)n * lg + (double)n) + 2.0 * (double)n) / 0.89;
+    cost += (double)n * ((double)nvars * 32.0 > 64.0e6 ? 25.0 : 5.5);
+  }
+  return cost;
 }
 
 static int shard_policy() {            // 0 = line, 1 = uniform, 2 = g2own
@@ -389,68 +421,128 @@ static int shard_policy() {            // 0 = line, 1 = uniform, 2 = g2own
   return v;
 }
 
-// ranks [0, G) share the line [H (+ quotient) | arrays...]; out[k] receives the ranges
-static void plan_line(size_t nvars, size_t n, int G, const bool with_b2, std::vector<ShardPlan>& out, int first_rank) {
-  const double cost[4] = {msm_cost(nvars, false), msm_cost(nvars, false), msm_cost(nvars, false),
-                          with_b2 ? msm_cost(nvars, true) : 0.0};
-  const double Wh = msm_cost(n, false), Q = quotient_cost(n, nvars);
-  const double Ww = cost[0] + cost[1] + cost[2] + cost[3];
-  // number of H ranks
-  int best_m = 1;
-  double best = 1e300, bestL = 0.0;
-  for (int m = 1; m <= G; m++) {
-    const double Th = Q + Wh / m;
-    double L = (Ww + m * Th) / G, worst;
-    if (L >= Th) worst = L;
-    else if (m < G) {
-      L = Ww / (G - m);
-      worst = Th > L ? Th : L;
-    } else continue;
-    if (worst < best * 0.995) {          // ties go to fewer redundant quotients
-      best = worst;
-      best_m = m;
-      bestL = L;
-    }
-  }
-  const int m = best_m;
-  const double Th = Q + Wh / m;
-  // walk the witness arrays; cut positions are snapped to array boundaries when within 1/8 of one
-  double pos = 0.0;                      // position on the line of witness work, in cost units
-  size_t cur_arr = 0, cur_pt = 0;        // next unassigned point
+// A unit of the line: arrays that are cut at the same witness indices, so that both sides of a cut keep one sort
+// for all of them.  Arrays: 0 = A1, 1 = B1, 2 = C1, 3 = B2.
+struct LineUnit { int arr[3]; int narr; };
+struct LineOrder { LineUnit u[4]; int nu; };
+
+static void set_range(ShardPlan& p, int arr, size_t lo, size_t hi) {
+  size_t* l[4] = {&p.a1_lo, &p.b1_lo, &p.c1_lo, &p.b2_lo};
+  size_t* h[4] = {&p.a1_hi, &p.b1_hi, &p.c1_hi, &p.b2_hi};
+  *l[arr] = lo;
+  *h[arr] = hi;
+}
+
+// Ranks [0, G) walk the line: rank k < m starts with the k-th of m equal pieces of H, then takes points of the
+// current unit for as long as its modelled cost stays below L; the last rank takes what is left.  Returns the cost of
+// the slowest rank.
+static double fill_line(const LineOrder& ord, size_t nvars, size_t n, int G, int m, double L, std::vector<ShardPlan>& out) {
+  const size_t snap = nvars / 8;        // pieces below an eighth of an array are not worth a sort and a reduction
+  int cu = 0;                           // current unit
+  size_t cp = 0;                        // next unassigned witness index of the current unit
+  double worst = 0.0;
   for (int k = 0; k < G; k++) {
-    ShardPlan& p = out[first_rank + k];
+    ShardPlan& p = out[k];
+    memset(&p, 0, sizeof(p));
     if (k < m) shard_range(n, k, m, p.h_lo, p.h_hi);
-    double cap = k < m ? (bestL > Th ? bestL - Th : 0.0) : bestL;
-    if (k == G - 1) cap = 1e300;         // the last rank takes the remainder
-    double end = pos + cap;
-    size_t* lo[4] = {&p.a1_lo, &p.b1_lo, &p.c1_lo, &p.b2_lo};
-    size_t* hi[4] = {&p.a1_hi, &p.b1_hi, &p.c1_hi, &p.b2_hi};
-    while (cur_arr < 4 && pos < end) {
-      if (cost[cur_arr] <= 0.0) {
-        cur_arr++;
-        cur_pt = 0;
-        continue;
+    const bool last = k == G - 1;
+    while (cu < ord.nu) {
+      const LineUnit& u = ord.u[cu];
+      auto with = [&](size_t hi) {
+        ShardPlan q = p;
+        for (int i = 0; i < u.narr; i++) set_range(q, u.arr[i], cp, hi);
+        return q;
+      };
+      size_t take_hi = nvars;
+      if (!last && rank_cost(with(nvars), nvars, n) > L) {
+        size_t lo = cp, hi = nvars;     // cost(with(lo)) <= L or nothing fits, cost(with(hi)) > L
+        while (hi - lo > 1) {
+          const size_t mid = lo + (hi - lo) / 2;
+          if (rank_cost(with(mid), nvars, n) <= L) lo = mid;
+          else hi = mid;
+        }
+        take_hi = lo;
+        if (take_hi - cp <= snap) take_hi = cp;                               // a sliver: leave it to the next rank
+        else if (nvars - take_hi <= snap) {                                   // would leave a sliver behind
+          take_hi = rank_cost(with(nvars), nvars, n) <= L * 1.03 ? nvars : nvars - snap - 1;
+          if (take_hi - cp <= snap) take_hi = cp;
+        }
       }
-      const double per_pt = cost[cur_arr] / (double)nvars;
-      const double room = end - pos;
-      size_t take = nvars - cur_pt;
-      if ((double)take * per_pt > room) {
-        take = (size_t)(room / per_pt);
-        const size_t snap = nvars / 8;                                        // pieces below a tenth of an array: not worth a sort + reduction
-        if (take <= snap) take = 0;                                          // a sliver: leave it to the next rank
-        else if (nvars - (cur_pt + take) <= snap) take = nvars - cur_pt;     // would leave a sliver behind
+      if (take_hi == cp) break;
+      p = with(take_hi);
+      cp = take_hi;
+      if (cp == nvars) {
+        cu++;
+        cp = 0;
+      } else break;                     // this rank is full
+    }
+    const double c = rank_cost(p, nvars, n);
+    if (c > worst) worst = c;
+  }
+  return cu < ord.nu ? 1e300 : worst;
+}
+
+// best plan of `G` ranks for the arrays of `orders` (with_b2 = false: the G2 MSM is placed by the caller)
+static void plan_line(size_t nvars, size_t n, int G, const bool with_b2, std::vector<ShardPlan>& out) {
+  static const LineOrder kOrders[] = {
+      {{{{0}, 1}, {{1}, 1}, {{2}, 1}, {{3}, 1}}, 4},          // H | A1 | B1 | C1 | B2
+      {{{{0, 1}, 2}, {{2}, 1}, {{3}, 1}}, 3},                 // H | A1+B1 | C1 | B2
+      {{{{2}, 1}, {{3}, 1}, {{0, 1}, 2}}, 3},                 // H | C1 | B2 | A1+B1
+      {{{{2}, 1}, {{0, 1}, 2}, {{3}, 1}}, 3},                 // H | C1 | A1+B1 | B2
+      {{{{0, 1, 2}, 3}, {{3}, 1}}, 2},                        // H | A1+B1+C1 | B2
+      {{{{3}, 1}, {{2}, 1}, {{0, 1}, 2}}, 3},                 // H | B2 | C1 | A1+B1
+  };
+  ShardPlan whole;
+  memset(&whole, 0, sizeof(whole));
+  whole.a1_hi = whole.b1_hi = whole.c1_hi = nvars;
+  if (with_b2) whole.b2_hi = nvars;
+  whole.h_hi = n;
+  const double all = rank_cost(whole, nvars, n);
+  double best = 1e300;
+  std::vector<ShardPlan> cand((size_t)G);
+  for (const LineOrder& full : kOrders) {
+    LineOrder ord = full;
+    if (!with_b2) {                      // drop the B2 unit
+      ord.nu = 0;
+      for (int i = 0; i < full.nu; i++)
+        if (full.u[i].arr[0] != 3) ord.u[ord.nu++] = full.u[i];
+    }
+    for (int m = 1; m <= G && m <= 8; m++) {
+      double lo = all / (double)G * 0.5, hi = all * 1.05;
+      for (int it = 0; it < 28; it++) {
+        const double L = 0.5 * (lo + hi);
+        const double worst = fill_line(ord, nvars, n, G, m, L, cand);
+        // ties go to the earlier order and to fewer redundant quotients
+        if (worst < best * 0.99) {
+          best = worst;
+          out = cand;
+        }
+        if (worst <= L * 1.03) hi = L;
+        else lo = L;
       }
-      if (take == 0) break;
-      *lo[cur_arr] = cur_pt;
-      *hi[cur_arr] = cur_pt + take;
-      pos += (double)take * per_pt;
-      cur_pt += take;
-      if (cur_pt == nvars) {
-        cur_arr++;
-        cur_pt = 0;
-      } else break;                      // this rank is full
     }
   }
+}
+
+// the search costs a few hundred thousand model evaluations: keep the plans of the last few (key, G) seen
+struct PlanCacheEntry { size_t nvars, n; int G, policy; std::vector<ShardPlan> plan; };
+static std::mutex g_plan_mu;
+static std::vector<PlanCacheEntry> g_plan_cache;
+static bool plan_cache_get(size_t nvars, size_t n, int G, int policy, std::vector<ShardPlan>& out) {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  for (auto& e : g_plan_cache)
+    if (e.nvars == nvars && e.n == n && e.G == G && e.policy == policy) {
+      out = e.plan;
+      return true;
+    }
+  return false;
+}
+static void plan_cache_put(size_t nvars, size_t n, int G, int policy, const std::vector<ShardPlan>& plan) {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  for (auto& e : g_plan_cache)
+    if (e.nvars == nvars && e.n == n && e.G == G && e.policy == policy) return;
+  if (g_plan_cache.size() >= 16) g_plan_cache.erase(g_plan_cache.begin());
+  g_plan_cache.push_back({nvars, n, G, policy, plan});
 }
 
 void shard_plan(size_t nvars, size_t npubs, size_t n, int k, int G, ShardPlan& out) {
@@ -466,14 +558,34 @@ void shard_plan(size_t nvars, size_t npubs, size_t n, int k, int G, ShardPlan& o
       p.b1_hi = p.c1_hi = p.b2_hi = p.a1_hi;
       shard_range(n, r, G, p.h_lo, p.h_hi);
     }
+  } else if (plan_cache_get(nvars, n, G, policy, all)) {
   } else if (policy == 2) {
-    plan_line(nvars, n, G - 1, false, all, 0);
+    std::vector<ShardPlan> head((size_t)(G - 1));
+    plan_line(nvars, n, G - 1, false, head);
+    for (int r = 0; r + 1 < G; r++) all[r] = head[r];
     all[G - 1].b2_lo = 0;
     all[G - 1].b2_hi = nvars;
   } else {
-    plan_line(nvars, n, G, true, all, 0);
+    plan_line(nvars, n, G, true, all);
   }
+  if (G > 1 && policy != 1) plan_cache_put(nvars, n, G, policy, all);
+  if (k == 0 && G > 1 && getenv("G16_PLAN_DEBUG"))       // modelled busy time per rank, ms at the B200 modmul peak
+    for (int r = 0; r < G; r++) fprintf(stderr, "[g16] plan rank %d of %d: model %.3f ms\n", r, G, rank_cost(all[r], nvars, n) / 6.76e7);
   out = all[k];
+  // experiment knob (tools/shape_probe.py): ten fractions a1_lo,a1_hi,b1_lo,b1_hi,c1_lo,c1_hi,b2_lo,b2_hi,h_lo,h_hi
+  // replace the plan of whatever rank is asked for -- used to time single shard shapes when fitting the cost model
+  if (const char* e = G > 1 ? getenv("G16_SHARD_SHAPE") : nullptr) {
+    double f[10];
+    if (sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf,%lf,%lf,%lf,%lf", f, f + 1, f + 2, f + 3, f + 4, f + 5, f + 6, f + 7, f + 8,
+               f + 9) == 10) {
+      size_t* dst[10] = {&out.a1_lo, &out.a1_hi, &out.b1_lo, &out.b1_hi, &out.c1_lo,
+                         &out.c1_hi, &out.b2_lo, &out.b2_hi, &out.h_lo,  &out.h_hi};
+      for (int i = 0; i < 10; i++) {
+        const double v = f[i] < 0.0 ? 0.0 : f[i] > 1.0 ? 1.0 : f[i];
+        *dst[i] = (size_t)(v * (double)(i < 8 ? nvars : n) + 0.5);
+      }
+    }
+  }
 }
 
 // raw points of [lo, hi) -> temporary device buffer.  The copy is issued on the consumer's stream: a plain
