@@ -105,7 +105,7 @@ void MultiProver::submit(const void* witness, int form, int mem_kind, const uint
     // launches per proof each: eight devices are fed in the time of one
     std::vector<std::thread> workers;
     std::vector<std::exception_ptr> errors((size_t)G);
-    for (int k = G - 1; k >= 1; k--)      // the devices with the G2 work (the longest kernels) are the last of the plan
+    for (int k = G - 1; k >= 1; k--)
       workers.emplace_back([&, k] {
         try {
           fn(k);

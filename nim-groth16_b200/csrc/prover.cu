@@ -756,6 +756,15 @@ Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_
   int ncopied = 0;
   shard_plan(nvars, npubs, n, shard_index, shard_count, plan);
 
+  auto pick_c = [&](size_t npts) {
+    int c = msm_pick_window(npts, precomp);
+    if (const char* e = getenv("G16_C_DELTA")) {             // experiment knob: wider / narrower windows
+      c += atoi(e);
+      if (c < 4) c = 4;
+      if (c > 22) c = 22;
+    }
+    return c;
+  };
   // witness-indexed pieces grouped by range (same range -> one sorter run, fused G1 launches)
   struct Piece { int which; size_t lo, hi; };
   const Piece pieces[4] = {{0, plan.a1_lo, plan.a1_hi}, {1, plan.b1_lo, plan.b1_hi}, {2, plan.c1_lo, plan.c1_hi},
@@ -771,13 +780,7 @@ Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_
       g = groups.back().get();
       g->lo = pc.lo;
       g->hi = pc.hi;
-      int c = msm_pick_window(pc.hi - pc.lo, precomp);
-      if (const char* e = getenv("G16_C_DELTA")) {           // experiment knob: window of the sharded pieces
-        if (shard_count > 1) c += atoi(e);
-        if (c < 4) c = 4;
-        if (c > 22) c = 22;
-      }
-      g->geom = msm_geometry(pc.hi - pc.lo, c, precomp);
+      g->geom = msm_geometry(pc.hi - pc.lo, pick_c(pc.hi - pc.lo), precomp);
     }
     if (pc.which == 3) g->has_b2 = true;
     else g->which1[g->nsets1++] = pc.which;
@@ -787,7 +790,7 @@ Resident::Resident(const g16_zkey_view& zk, int shard_index_in, int shard_count_
   for (size_t i = 1; i < groups.size(); i++)
     if (groups[i]->has_b2) std::swap(groups[0], groups[i]);
   const size_t nh = plan.h_hi - plan.h_lo;
-  if (nh) gh = msm_geometry(nh, msm_pick_window(nh, precomp), precomp);
+  if (nh) gh = msm_geometry(nh, pick_c(nh), precomp);
 
   // uploads, validation and table building; one raw staging buffer per array and the copies on their own stream, so
   // that the H2D of the next array overlaps with the table kernel of the previous one (the buffers are released at
