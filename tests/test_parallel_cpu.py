@@ -167,3 +167,37 @@ def test_masked_shard_records_recombine_in_the_oracle(kat):
         for term in (o.g1_mul(s, zk.alpha1), o.g1_mul(r, zk.beta1), o.g1_mul(r * s % o.R, zk.delta1)):
             pi_c = o.g1_add(pi_c, term)
         assert (pi_a, pi_b, pi_c) == (want.pi_a, want.pi_b, want.pi_c), g
+
+
+def test_planned_ranks_are_balanced_by_the_fitted_model():
+    """The planner (prover.cu plan_line / rank_cost) balances the modelled busy time: at the benchmark sizes the
+    slowest rank of the default plan is within 16 % of the mean over ranks for 2, 4 and 8 GPUs, no rank owns a piece
+    smaller than an eighth of an array, and the plan is the same in every process (the ranks never exchange it)."""
+    import subprocess, sys, os, re, json
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nim-groth16_b200")
+    code = ("import sys, json; sys.path.insert(0, %r); from g16b200.parallel import shard_plan\n"
+            "out = {}\n"
+            "for lg in (20, 22):\n"
+            "    for g in (2, 4, 8):\n"
+            "        out['%%d,%%d' %% (lg, g)] = [shard_plan(1 << lg, 1, 1 << lg, k, g) for k in range(g)]\n"
+            "print(json.dumps(out))" % pkg)
+    env = dict(os.environ, G16_PLAN_DEBUG="1")
+    env.pop("G16_SHARD_POLICY", None)
+    runs = [subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, check=True)
+            for _ in range(2)]
+    assert runs[0].stdout == runs[1].stdout
+    plans = json.loads(runs[0].stdout)
+    model = {}
+    for m in re.finditer(r"plan rank (\d+) of (\d+): model ([0-9.]+) ms", runs[0].stderr):
+        model.setdefault(int(m.group(2)), []).append(float(m.group(3)))
+    # the debug lines of the two sizes follow each other per world size: 2^20 first
+    for g in (2, 4, 8):
+        assert len(model[g]) == 2 * g
+        for costs in (model[g][:g], model[g][g:]):
+            assert max(costs) <= 1.16 * sum(costs) / g, (g, costs)
+    for key, ranks in plans.items():
+        lg = int(key.split(",")[0])
+        for p in ranks:
+            for nm in ("a1", "b1", "c1", "b2"):
+                size = p[nm + "_hi"] - p[nm + "_lo"]
+                assert size == 0 or size > (1 << lg) // 8, (key, p)
