@@ -45,6 +45,11 @@ cudaStream_t pool_stream() {
     uint64_t keep = ~0ull;
     if (const char* e = getenv("G16_POOL_KEEP_MB")) keep = (uint64_t)atoll(e) << 20;   // 0: give memory back on free
     G16_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    // experiment knob: L2 fetch granularity in bytes (32 / 64 / 128).  The bucket accumulation gathers 64-byte table
+    // entries at random; ncu shows 2x the algorithmic DRAM bytes for it (profiles/ncu_traffic.json)
+    if (const char* e = getenv("G16_L2_FETCH")) {
+      if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)) != cudaSuccess) cudaGetLastError();
+    }
   }
   return streams[dev];
 }
