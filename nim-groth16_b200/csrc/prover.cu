@@ -584,6 +584,7 @@ void shard_plan(size_t nvars, size_t npubs, size_t n, int k, int G, ShardPlan& o
         const double v = f[i] < 0.0 ? 0.0 : f[i] > 1.0 ? 1.0 : f[i];
         *dst[i] = (size_t)(v * (double)(i < 8 ? nvars : n) + 0.5);
       }
+      if (getenv("G16_PLAN_DEBUG")) fprintf(stderr, "[g16] shape model %.4f ms\n", rank_cost(out, nvars, n) / 6.76e7);
     }
   }
 }

@@ -201,3 +201,33 @@ def test_planned_ranks_are_balanced_by_the_fitted_model():
             for nm in ("a1", "b1", "c1", "b2"):
                 size = p[nm + "_hi"] - p[nm + "_lo"]
                 assert size == 0 or size > (1 << lg) // 8, (key, p)
+
+
+def test_cost_model_reproduces_the_measured_shard_shapes():
+    """rank_cost (prover.cu) against the committed measurements it was fitted to (profiles/r2_v9_shape_probe.log, busy
+    time of 73 shard shapes on one B200 with two proofs in flight): every shape within 10 %, rms below 0.2 ms.  Runs in
+    a child process because the debug line goes to the C library's stderr."""
+    import subprocess, sys, os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shapes = []
+    for line in open(os.path.join(root, "profiles", "r2_v9_shape_probe.log")):
+        m = re.match(r"shape (.+?)\s+([-0-9.,e]+)\s+([0-9.]+) ms", line)
+        if m:
+            shapes.append((m.group(1).strip(), m.group(2), float(m.group(3))))
+    assert len(shapes) >= 70
+    code = ("import sys, os; sys.path.insert(0, %r)\n"
+            "from g16b200.parallel import shard_plan\n"
+            "for sh in sys.argv[1:]:\n"
+            "    os.environ['G16_SHARD_SHAPE'] = sh\n"
+            "    shard_plan(1 << 20, 1, 1 << 20, 1, 2)\n" % os.path.join(root, "nim-groth16_b200"))
+    env = dict(os.environ, G16_PLAN_DEBUG="1")
+    env.pop("G16_SHARD_POLICY", None)
+    run = subprocess.run([sys.executable, "-c", code] + [s[1] for s in shapes], capture_output=True, text=True, env=env,
+                         check=True)
+    model = [float(v) for v in re.findall(r"shape model ([0-9.]+) ms", run.stderr)]
+    assert len(model) == len(shapes)
+    sq = 0.0
+    for (name, _, meas), mod in zip(shapes, model):
+        assert abs(mod - meas) <= 0.10 * meas, (name, meas, mod)
+        sq += (mod - meas) ** 2
+    assert (sq / len(shapes)) ** 0.5 < 0.2
